@@ -1,0 +1,64 @@
+"""Shared test-case definitions (the time-dependent callables used when the
+golden fixtures were generated, see tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + '.npz'))
+
+
+def theta_t(t):
+    return .2 + .1*t
+
+
+def hw_theta(t):
+    return np.array(((.02 + .001*t,), (0.,), (0.,)))
+
+
+def hw_corr(t):
+    c01, c02, c12 = .3*np.cos(t), -.2 + .05*t, .1
+    return np.array(((1, c01, c02), (c01, 1, c12), (c02, c12, 1)))
+
+
+HW = dict(factors=3, x0=((.01,), (0.,), (0.,)), theta=hw_theta,
+          k=((.1,), (.5,), (1.,)), sigma=((.01,), (.008,), (.005,)),
+          corr=hw_corr)
+HESTON = dict(x0=100., mu=.03, sigma=1., y0=.04, theta=.04, k=2., xi=.3,
+              rho=-.7)
+MERTON = dict(x0=1., mu=.05, sigma=.2, lam=2., a=-.1, b=.15)
+KOU = dict(x0=1., mu=.05, sigma=.2, lam=2., a=.1, b=.15, pa=.4)
+
+# name -> (oracle model, params for the sde, extra kwargs) for replay fixtures
+REPLAY = {
+    'replay_wiener': ('wiener', dict(mu=.1, sigma=.7), dict(x0=.5)),
+    'replay_lognorm': ('lognorm', dict(mu=.05, sigma=.2), dict(x0=1.)),
+    'replay_lognorm_v3': ('lognorm',
+                          dict(mu=((.05,), (.0,), (-.1,)),
+                               sigma=((.2,), (.3,), (.1,))),
+                          dict(x0=((1.,), (2.,), (3.,)))),
+    'replay_oruh_tdep': ('ornstein_uhlenbeck',
+                         dict(theta=theta_t, k=1., sigma=.3), dict(x0=.1)),
+    'replay_hw3_tdep': ('hull_white',
+                        dict(theta=hw_theta, k=HW['k'], sigma=HW['sigma']),
+                        dict(x0=HW['x0'])),
+    'replay_cir': ('cox_ingersoll_ross', dict(theta=.04, k=1.5, xi=.6),
+                   dict(x0=.05)),
+    'replay_heston': ('heston',
+                      dict(mu=.03, sigma=1., theta=.04, k=2., xi=.9),
+                      dict(x0=100., y0=.04)),
+    'replay_heston_full': ('heston',
+                           dict(mu=.03, sigma=1., theta=.04, k=2., xi=.3),
+                           dict(x0=100., y0=.04, full=True)),
+    'replay_heston_v2': ('heston',
+                         dict(mu=.03, sigma=1., theta=.04, k=2.,
+                              xi=((.3,), (1.1,))),
+                         dict(x0=((100.,), (50.,)), y0=.04, full=True)),
+    'replay_merton': ('jumpdiff', dict(mu=.05, sigma=.2), dict(x0=1.)),
+    'replay_kou': ('jumpdiff', dict(mu=.05, sigma=.2), dict(x0=1.)),
+    'replay_oruh_ragged': ('ornstein_uhlenbeck',
+                           dict(theta=.5, k=2., sigma=.4), dict(x0=1.)),
+}

@@ -1,0 +1,225 @@
+"""
+Generate the golden fixtures under tests/golden/ by RUNNING THE UNMODIFIED
+REFERENCE (/root/reference/sdepy).  Run once in the authoring container:
+
+    python tests/golden/make_golden.py
+
+The reference is only importable there; the fixtures (small .npz files)
+travel with the repo and pin both the CPU oracle (tests/test_oracle_golden.py,
+no GPU) and the CUDA path (tests/test_gpu_parity.py, -m gpu).
+
+Two kinds of fixtures:
+
+* ``replay_*``: the reference integrates a preset process while a recording
+  wrapper (obeying the reference's source protocol, infrastructure.py:
+  1321-1330) logs every increment its own sources return.  Stored: the
+  parameters, timeline, merged step grid, the logged increments, the
+  reference output and ``info`` counters.
+* ``seeded_*``: plain same-seed runs (``rng=np.random.default_rng(seed)``),
+  storing only inputs and outputs -- these pin the oracle's restatement of
+  the sources' generator consumption.
+* ``stats_*``: ``process.pmean/pvar/pstd`` and ``montecarlo`` results.
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, '/root/reference')
+import sdepy  # noqa: E402
+from sdepy import infrastructure as infra  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class recorder:
+    """Source-protocol wrapper logging (t, dt, value[, dn_value])."""
+
+    def __init__(self, inner):
+        self.inner = inner
+        self.paths, self.vshape = inner.paths, inner.vshape
+        self.t, self.dt, self.dz, self.dn = [], [], [], []
+        self._has_dn = False
+
+    def __call__(self, t, dt):
+        z = self.inner(t, dt)
+        self.t.append(float(t)); self.dt.append(float(dt))
+        self.dz.append(np.array(z))
+        if hasattr(self.inner, 'dn_value'):
+            # forwarded because jumpdiff_SDE.info_next probes it
+            # (integration.py:2615)
+            self.dn_value = self.inner.dn_value
+            self.dn.append(np.array(self.inner.dn_value))
+        return z
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **arrays)
+    print('%-34s %7.1f KB' % (name, os.path.getsize(path)/1024))
+
+
+def grid_of(P, timeline):
+    tt = np.asarray(timeline, dtype=float)
+    target = P.pace(tt)
+    target = target[(target >= tt[0]) & (target <= tt[-1])]
+    return np.unique(np.concatenate((target, tt)))
+
+
+def replay_case(name, cls, timeline, paths, steps, vshape=(), seed=7,
+                jumps=False, **params):
+    rng = np.random.default_rng(seed)
+    probe = cls(paths=paths, vshape=vshape, steps=steps, rng=rng, **params)
+    rec_w = recorder(probe.sources['dw'])
+    kw = dict(dw=rec_w)
+    if jumps:
+        rec_j = recorder(probe.sources['dj'])
+        kw['dj'] = rec_j
+    # second instance consuming the recording wrappers
+    src_keys = ('corr', 'rho', 'lam', 'a', 'b', 'pa', 'y', 'ptype')
+    P = cls(paths=paths, vshape=vshape, steps=steps,
+            **{k: v for k, v in params.items() if k not in src_keys}, **kw)
+    out = P(timeline)
+    outs = out if isinstance(out, tuple) else (out,)
+    arrays = dict(tt=np.asarray(timeline, dtype=float),
+                  grid=grid_of(P, timeline),
+                  dW=np.stack(rec_w.dz), t=np.array(rec_w.t),
+                  dt=np.array(rec_w.dt))
+    for i, o in enumerate(outs):
+        arrays['out%d' % i] = np.asarray(o)
+    if jumps:
+        arrays['dJ'] = np.stack(rec_j.dz)
+        arrays['dN'] = np.stack(rec_j.dn)
+        arrays['jump_count'] = P.info['jump_count']
+        arrays['jump_rate'] = P.info['jump_rate']
+    if 'negative_y_count' in P.info:
+        arrays['negative_y_count'] = P.info['negative_y_count']
+    arrays['computed_steps'] = np.array(P.info['computed_steps'])
+    arrays['stored_steps'] = np.array(P.info['stored_steps'])
+    for k, v in params.items():
+        if not callable(v):
+            arrays['p_' + k] = np.asarray(v)
+    save(name, **arrays)
+
+
+def seeded_case(name, cls, timeline, paths, steps, seed, vshape=(), **params):
+    P = cls(paths=paths, vshape=vshape, steps=steps,
+            rng=np.random.default_rng(seed), **params)
+    out = P(timeline)
+    outs = out if isinstance(out, tuple) else (out,)
+    arrays = dict(tt=np.asarray(timeline, dtype=float), seed=np.array(seed))
+    for i, o in enumerate(outs):
+        arrays['out%d' % i] = np.asarray(o)
+    for k in ('negative_y_count', 'jump_count', 'jump_rate'):
+        if k in P.info:
+            arrays[k] = P.info[k]
+    save(name, **arrays)
+
+
+def theta_t(t):
+    return .2 + .1*t
+
+
+def hw_theta(t):
+    return np.array(((.02 + .001*t,), (0.,), (0.,)))
+
+
+def hw_corr(t):
+    c01, c02, c12 = .3*np.cos(t), -.2 + .05*t, .1
+    return np.array(((1, c01, c02), (c01, 1, c12), (c02, c12, 1)))
+
+
+HW = dict(factors=3, x0=((.01,), (0.,), (0.,)), theta=hw_theta,
+          k=((.1,), (.5,), (1.,)), sigma=((.01,), (.008,), (.005,)),
+          corr=hw_corr)
+HESTON = dict(x0=100., mu=.03, sigma=1., y0=.04, theta=.04, k=2., xi=.3,
+              rho=-.7)
+MERTON = dict(x0=1., mu=.05, sigma=.2, lam=2., a=-.1, b=.15)
+KOU = dict(x0=1., mu=.05, sigma=.2, lam=2., a=.1, b=.15, pa=.4)
+
+
+def main():
+    P = 193  # deliberately not a multiple of 32
+    # ---- replay fixtures (BASELINE.json configs, scaled down) ------------
+    replay_case('replay_wiener', sdepy.wiener_process, np.linspace(0, 1, 6),
+                P, 21, x0=.5, mu=.1, sigma=.7)
+    replay_case('replay_lognorm', sdepy.lognorm_process,
+                np.linspace(0, 1, 11), P, 41, x0=1., mu=.05, sigma=.2)
+    replay_case('replay_lognorm_v3', sdepy.lognorm_process,
+                (0., .3, 1.), 67, 17, vshape=(3,), x0=((1.,), (2.,), (3.,)),
+                mu=((.05,), (.0,), (-.1,)), sigma=((.2,), (.3,), (.1,)),
+                corr=((1, .5, -.2), (.5, 1, .1), (-.2, .1, 1)))
+    replay_case('replay_oruh_tdep', sdepy.ornstein_uhlenbeck_process,
+                np.linspace(0, 5, 11), P, 51, x0=.1, theta=theta_t, k=1.,
+                sigma=.3)
+    replay_case('replay_hw3_tdep', sdepy.hull_white_process,
+                np.linspace(0, 5, 11), P, 51, **HW)
+    replay_case('replay_cir', sdepy.cox_ingersoll_ross_process,
+                np.linspace(0, 2, 5), P, 81, x0=.05, theta=.04, k=1.5, xi=.6)
+    replay_case('replay_heston', sdepy.heston_process, (0., 1.), P,
+                np.linspace(0, 1, 64), **dict(HESTON, xi=.9))
+    replay_case('replay_heston_full', sdepy.full_heston_process,
+                np.linspace(0, 1, 5), P, 33, **HESTON)
+    replay_case('replay_heston_v2', sdepy.full_heston_process,
+                (0., .5, 1.), 67, 21, vshape=(2,),
+                **dict(HESTON, x0=((100.,), (50.,)), rho=(-.7, .2),
+                       xi=((.3,), (1.1,))))
+    replay_case('replay_merton', sdepy.merton_jumpdiff_process,
+                np.linspace(0, 1, 5), P, 101, jumps=True,
+                **dict(MERTON, lam=20.))
+    replay_case('replay_kou', sdepy.kou_jumpdiff_process,
+                np.linspace(0, 1, 5), P, 101, jumps=True,
+                **dict(KOU, lam=20.))
+    # uneven grid: explicit step points not aligned with the timeline
+    replay_case('replay_oruh_ragged', sdepy.ornstein_uhlenbeck_process,
+                (0., .37, 1.), 5, (0.1, .2, .21, .5, .93, 1.5), x0=1.,
+                theta=.5, k=2., sigma=.4)
+
+    # ---- same-seed fixtures ---------------------------------------------
+    seeded_case('seeded_lognorm', sdepy.lognorm_process, (0., .5, 1.), 101,
+                30, 11, x0=1., mu=.05, sigma=.2)
+    seeded_case('seeded_hw3_tdep', sdepy.hull_white_process, (0., 2.5, 5.),
+                101, 26, 12, **HW)
+    seeded_case('seeded_heston', sdepy.heston_process, (0., 1.), 101, 50, 13,
+                **HESTON)
+    seeded_case('seeded_merton', sdepy.merton_jumpdiff_process, (0., 1.), 101,
+                80, 14, **dict(MERTON, lam=15.))
+    seeded_case('seeded_kou', sdepy.kou_jumpdiff_process, (0., 1.), 101, 80,
+                15, **dict(KOU, lam=15.))
+
+    # ---- statistics -------------------------------------------------------
+    rng = np.random.default_rng(21)
+    x = sdepy.lognorm_process(paths=4001, steps=20, rng=rng, x0=1., mu=.05,
+                              sigma=.2, vshape=(2,))((0., .5, 1.))
+    mc1 = sdepy.montecarlo(x[-1], bins=25)
+    a = sdepy.montecarlo(bins=25)
+    chunks = (x[-1][:, :1500], x[-1][:, 1500:2700], x[-1][:, 2700:])
+    for c in chunks:
+        a.update(c)
+    arrays = dict(x=np.asarray(x), t=x.t,
+                  pmean=np.asarray(x.pmean()), pvar=np.asarray(x.pvar()),
+                  pstd=np.asarray(x.pstd()), pvar1=np.asarray(x.pvar(ddof=1)))
+    for tag, m in (('one', mc1), ('chunk', a)):
+        arrays.update({
+            tag + '_mean': m.mean(), tag + '_var': m.var(),
+            tag + '_std': m.std(), tag + '_stderr': m.stderr(),
+            tag + '_skew': m.skew(), tag + '_kurt': m.kurtosis(),
+            tag + '_counts': np.stack([m[i].histogram()[0] for i in range(2)]),
+            tag + '_edges': np.stack([m[i].histogram()[1] for i in range(2)]),
+            tag + '_outpaths': np.stack([m[i].outpaths for i in range(2)]),
+        })
+    save('stats_lognorm', **arrays)
+
+    # the reference's own known-answer check: Euler on log x is exact for
+    # constant-parameter lognormal on shared increments
+    # (sdepy/tests/test_processes.py:681-708)
+    t = np.linspace(0, 1, 9)
+    dw = sdepy.true_wiener_source(paths=31, rng=np.random.default_rng(3))
+    xe = sdepy.lognorm_process(paths=31, x0=1., mu=.05, sigma=.2, dw=dw)(t)
+    w = dw(t) - dw(0.)  # realised Brownian path
+    save('known_lognorm_exact', t=t, w=np.asarray(w), x=np.asarray(xe),
+         dW=np.diff(np.asarray(dw(t)), axis=0))
+
+
+if __name__ == '__main__':
+    main()

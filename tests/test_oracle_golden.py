@@ -1,0 +1,129 @@
+"""CPU tests: the oracle (oracle/sde_oracle.py) reproduces every golden
+fixture generated from the unmodified reference BIT-EXACTLY."""
+import numpy as np
+import pytest
+
+from oracle import sde_oracle as orc
+from tests.cases import (golden, REPLAY, HW, hw_corr, MERTON, KOU)
+
+
+@pytest.mark.parametrize('name', sorted(REPLAY))
+def test_replay_bit_exact(name):
+    g = golden(name)
+    model, params, kw = REPLAY[name]
+    where = np.searchsorted(g['grid'], g['tt'])
+    # the recorded (t, dt) are what the oracle's grid walk must visit
+    assert np.array_equal(g['t'], g['grid'][:-1])
+    assert np.array_equal(g['dt'], g['grid'][1:] - g['grid'][:-1])
+    dJ = g['dJ'] if 'dJ' in g else None
+    dN = g['dN'] if 'dN' in g else None
+    out, info = orc.euler_replay(model, params, kw['x0'], g['grid'], where,
+                                 g['dW'], dJ, dN, y0=kw.get('y0'),
+                                 full=kw.get('full', False))
+    outs = out if isinstance(out, tuple) else (out,)
+    for i, o in enumerate(outs):
+        ref = g['out%d' % i]
+        assert o.shape == ref.shape
+        assert np.array_equal(o, ref), name
+    for key in ('negative_y_count', 'jump_count'):
+        if key in g:
+            assert np.array_equal(info[key], g[key])
+    assert int(g['computed_steps']) == g['grid'].size - 1
+    assert int(g['stored_steps']) == g['tt'].size - 1
+
+
+def test_step_grid_matches_reference_merge():
+    for name in sorted(REPLAY):
+        g = golden(name)
+    g = golden('replay_oruh_ragged')
+    tt, grid, where = orc.step_grid((0., .37, 1.),
+                                    (0.1, .2, .21, .5, .93, 1.5))
+    assert np.array_equal(grid, g['grid'])
+    g = golden('replay_lognorm')
+    tt, grid, where = orc.step_grid(np.linspace(0, 1, 11), 41)
+    assert np.array_equal(grid, g['grid'])
+    assert np.array_equal(grid[where], tt)
+
+
+def test_seeded_lognorm():
+    g = golden('seeded_lognorm')
+    out, _ = orc.self_driven('lognorm', dict(mu=.05, sigma=.2), 1., g['tt'],
+                             30, 101, np.random.default_rng(int(g['seed'])))
+    assert np.array_equal(out, g['out0'])
+
+
+def test_seeded_hw3_time_dependent_corr():
+    g = golden('seeded_hw3_tdep')
+    out, _ = orc.self_driven(
+        'hull_white', dict(theta=HW['theta'], k=HW['k'], sigma=HW['sigma']),
+        HW['x0'], g['tt'], 26, 101, np.random.default_rng(int(g['seed'])),
+        wshape=(3,), corr=hw_corr)
+    assert np.array_equal(out, g['out0'])
+
+
+def test_seeded_heston():
+    g = golden('seeded_heston')
+    out, info = orc.self_driven(
+        'heston', dict(mu=.03, sigma=1., theta=.04, k=2., xi=.3), 100.,
+        g['tt'], 50, 101, np.random.default_rng(int(g['seed'])),
+        wshape=(2,), corr=orc.rho_to_corr(-.7), y0=.04)
+    assert np.array_equal(out, g['out0'])
+    assert np.array_equal(info['negative_y_count'], g['negative_y_count'])
+    # memory-light streaming variant used as bench cpu baseline
+    tt, grid, where = orc.step_grid(g['tt'], 50)
+    xT, neg = orc.heston_stream(
+        dict(mu=.03, sigma=1., theta=.04, k=2., xi=.3), 100., .04, -.7, grid,
+        101, np.random.default_rng(int(g['seed'])))
+    assert np.array_equal(xT, g['out0'][-1])
+    assert np.array_equal(neg, g['negative_y_count'])
+
+
+@pytest.mark.parametrize('name,law', [
+    ('seeded_merton', ('norm', dict(a=MERTON['a'], b=MERTON['b']))),
+    ('seeded_kou', ('double_exp', dict(a=KOU['a'], b=KOU['b'], pa=KOU['pa']))),
+])
+def test_seeded_jumps(name, law):
+    g = golden(name)
+    out, info = orc.self_driven(
+        'jumpdiff', dict(mu=.05, sigma=.2), 1., g['tt'], 80, 101,
+        np.random.default_rng(int(g['seed'])), lam=15.,
+        law=orc.jump_law(law[0], **law[1]))
+    assert np.array_equal(out, g['out0'])
+    assert np.array_equal(info['jump_count'], g['jump_count'])
+
+
+def test_stats_against_reference():
+    g = golden('stats_lognorm')
+    x = g['x']
+    assert np.array_equal(orc.pmean(x), g['pmean'])
+    assert np.array_equal(orc.pvar(x), g['pvar'])
+    assert np.array_equal(orc.pstd(x), g['pstd'])
+    assert np.array_equal(orc.pvar(x, ddof=1), g['pvar1'])
+    one = orc.moments_histogram(bins=25)
+    one.update(x[-1])
+    chunk = orc.moments_histogram(bins=25)
+    for c in (x[-1][:, :1500], x[-1][:, 1500:2700], x[-1][:, 2700:]):
+        chunk.update(c)
+    for tag, m in (('one', one), ('chunk', chunk)):
+        assert np.array_equal(m.mean(), g[tag + '_mean'])
+        assert np.array_equal(m.var(), g[tag + '_var'])
+        assert np.array_equal(m.std(), g[tag + '_std'])
+        assert np.array_equal(m.stderr(), g[tag + '_stderr'])
+        assert np.array_equal(m.skew(), g[tag + '_skew'])
+        assert np.array_equal(m.kurtosis(), g[tag + '_kurt'])
+        assert np.array_equal(np.stack(m.counts), g[tag + '_counts'])
+        assert np.array_equal(np.stack(m.edges), g[tag + '_edges'])
+        assert np.array_equal(np.array(m.outside), g[tag + '_outpaths'])
+
+
+def test_known_answer_lognorm_exact():
+    """The reference's own known-answer test (sdepy/tests/test_processes.py:
+    681-708): Euler on log x is exact for constant parameters."""
+    g = golden('known_lognorm_exact')
+    t = g['t']
+    tt, grid, where = orc.step_grid(t, None)
+    out, _ = orc.euler_replay('lognorm', dict(mu=.05, sigma=.2), 1., grid,
+                              where, g['dW'])
+    exact = np.exp((.05 - .2*.2/2)*t[:, None] + .2*g['w'])
+    assert np.allclose(out, exact, rtol=16*np.finfo(float).resolution)
+    assert np.allclose(out, g['x'], rtol=1e-13)
