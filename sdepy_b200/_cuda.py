@@ -1,0 +1,83 @@
+"""Device plumbing: torch owns device memory and streams, libsdeb does the work.
+
+PyTorch is used here only for allocation, H2D/D2H copies, the current-stream
+handle and (in ``distributed``) NCCL; no torch operator is on the compute path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            'sdepy_b200 needs a CUDA device (B200, sm_100a): there is no CPU '
+            'fallback for the integration / statistics kernels')
+
+
+def device(dev=None):
+    require_cuda()
+    if dev is None:
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device(dev)
+
+
+def stream_ptr(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def to_device(a, dev, dtype=None):
+    """Host ndarray -> device tensor through pinned memory (async H2D)."""
+    a = np.ascontiguousarray(a, dtype=dtype)
+    t = torch.from_numpy(a)
+    if a.size:
+        t = t.pin_memory()
+    return t.to(dev, non_blocking=True)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def empty(shape, dev, dtype=torch.float64):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+def zeros(shape, dev, dtype=torch.float64):
+    return torch.zeros(shape, dtype=dtype, device=dev)
+
+
+def moments(x2d, n_paths, centre=None):
+    """Power sums / min / max over the last axis of a device tensor viewed as
+    [rows, pitch] (sdeb_moments).  Returns a host array [rows, NSTAT]."""
+    dev = x2d.device
+    rows, pitch = x2d.shape
+    out = np.empty((rows, _lib.NSTAT))
+    for r0 in range(0, rows, 32768):
+        r1 = min(rows, r0 + 32768)
+        n = r1 - r0
+        ws_bytes = _lib.lib.sdeb_moments_workspace(n)
+        ws = empty((ws_bytes // 8,), dev)
+        stats = empty((n, _lib.NSTAT), dev)
+        c = None
+        if centre is not None:
+            c = to_device(np.asarray(centre, dtype=float).reshape(-1)[r0:r1], dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.sdeb_moments(
+                ptr(x2d[r0:r1]), n, n_paths, pitch, ptr(c), ptr(stats), ptr(ws),
+                ws_bytes, stream_ptr(dev)))
+        out[r0:r1] = stats.cpu().numpy()
+    return out
+
+
+def histogram(x1d, edges, counts, outside, uniform):
+    """counts/outside (device int64 tensors) += histogram of x1d on edges."""
+    dev = x1d.device
+    e = to_device(np.asarray(edges, dtype=float), dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.sdeb_histogram(
+            ptr(x1d), x1d.numel(), ptr(e), len(edges) - 1, int(bool(uniform)),
+            ptr(counts), ptr(outside), stream_ptr(dev)))

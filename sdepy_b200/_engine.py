@@ -1,0 +1,272 @@
+"""Launch builder: turns a lowered SDE problem into ``sdeb_integrate`` calls.
+
+Everything here is host-side table building (the reference's one-time setup,
+``integration.py:506-563``) plus pointer plumbing; the stepping itself is the
+fused kernel of ``csrc/sde_engine.cuh``.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cuda, _lib
+
+
+class segment:
+    """One monotone sweep of the step grid (forward, or backward when the
+    integration starts from an inner point, integration.py:573-580)."""
+
+    def __init__(self, s, ds, store_row, row0, step_base):
+        self.s = np.asarray(s, dtype=float)          # left time of each step
+        self.ds = np.asarray(ds, dtype=float)        # signed step
+        self.store_row = np.asarray(store_row, dtype=np.int32)
+        self.row0 = int(row0)
+        self.step_base = int(step_base)              # Philox step offset
+
+    @property
+    def n_steps(self):
+        return self.ds.size
+
+
+def segments_of(tt, grid, i0):
+    """Forward/backward sweeps from ``tt[i0]`` and the row each step stores
+    into (exact float equality, integration.py:386).  Returns the list of
+    segments and the number of stored steps."""
+    tt = np.asarray(tt, dtype=float)
+    grid = np.asarray(grid, dtype=float)
+    i0 = int(i0) % tt.size
+    row_of = {float(t): i for i, t in enumerate(tt)}
+    j0 = int(np.searchsorted(grid, tt[i0]))
+    assert grid[j0] == tt[i0]
+    segs = []
+    if i0 != 0:                                      # backward sweep
+        pts = grid[j0::-1]
+        rows = [row_of.get(float(t), -1) for t in pts[1:]]
+        segs.append(segment(pts[:-1], pts[1:] - pts[:-1], rows, i0, grid.size))
+    if i0 == 0 or i0 != tt.size - 1:                 # forward sweep
+        pts = grid[j0:]
+        rows = [row_of.get(float(t), -1) for t in pts[1:]]
+        segs.append(segment(pts[:-1], pts[1:] - pts[:-1], rows, i0, 0))
+    return segs
+
+
+class problem_spec:
+    """Static description of the kernel variant and lane decomposition."""
+
+    def __init__(self, model, ncomp, groups, jit_handle=0):
+        self.model, self.ncomp, self.groups = int(model), int(ncomp), int(groups)
+        self.jit_handle = int(jit_handle)
+        p = _lib.Problem()
+        p.abi_version = _lib.ABI_VERSION
+        p.model, p.ncomp, p.jit_handle = self.model, self.ncomp, self.jit_handle
+        p.n_groups, p.n_psteps = self.groups, 1
+        plan = _lib.plan(p)
+        self.nw, self.ndw, self.nx = plan.nw, plan.ndw, plan.nx
+        self.npc, self.npt, self.ncnt = plan.npc, plan.npt, plan.ncnt
+        self.jumps = bool(plan.jumps)
+        self.nchol = self.npt - self.npc
+
+
+def chol_entries(L, ndw):
+    """Row-major lower triangle of a Cholesky factor (identity if None)."""
+    if ndw <= 1:
+        return np.zeros(0)
+    if L is None:
+        L = np.eye(ndw)
+    return np.asarray(L, dtype=float)[np.tril_indices(ndw)]
+
+
+class run_result:
+    pass
+
+
+def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
+        dev=None, replay=None, want_out=True, want_stats=False, centre=None,
+        payoff=None, counters=False, dn_sums=False, dump=False, max_blocks=0):
+    """Run all segments.  ``records[k]`` is the parameter table of segment k,
+    shaped [1 or n_steps, groups, npt]; ``replay`` (optional) is a list of
+    dicts with device/host tables 'dW', 'dJ', 'dN' per segment.
+
+    Returns a ``run_result`` with device tensors ``out`` [n_rows, G*nx, paths],
+    ``stats`` [n_rows, G*nx, NSTAT], ``counter`` [G*ncnt, paths], host
+    ``dn_sum`` (list per segment) and, when ``dump``, the generated increments.
+    """
+    dev = _cuda.device(dev)
+    res = run_result()
+    gx = spec.groups*spec.nx
+    res.out = _cuda.empty((n_rows, gx, paths), dev) if want_out else None
+    if want_out:
+        # rows never reached stay NaN, like the reference's allocation
+        # (integration.py:550)
+        res.out.fill_(float('nan'))
+    res.stats = None
+    res.counter = (_cuda.zeros((spec.groups*spec.ncnt, paths), dev, torch.int64)
+                   if counters and spec.ncnt else None)
+    res.dn_sum, res.dump = [], []
+    stats_total = None
+    w0 = np.ascontiguousarray(w0, dtype=float)
+    w0_per_path = int(w0.ndim == 3)
+    w0_d = _cuda.to_device(w0, dev)
+    centre_d = None
+    if want_stats:
+        centre_d = _cuda.to_device(np.asarray(centre, dtype=float).reshape(gx), dev)
+
+    keep = []   # keep device buffers alive until the launches are enqueued
+    for k, seg in enumerate(segs):
+        n = seg.n_steps
+        rec = np.ascontiguousarray(records[k], dtype=float)
+        assert rec.shape[1:] == (spec.groups, spec.npt), (rec.shape, spec.groups, spec.npt)
+        p = _lib.Problem()
+        p.abi_version = _lib.ABI_VERSION
+        p.model, p.ncomp, p.jit_handle = spec.model, spec.ncomp, spec.jit_handle
+        p.noise = _lib.NOISE_REPLAY if replay is not None else _lib.NOISE_PHILOX
+        p.n_paths, p.path_offset, p.pitch = paths, path_offset, paths
+        p.n_steps, p.n_groups, p.n_rows = n, spec.groups, n_rows
+        p.row0 = seg.row0 if k == 0 else -1
+        p.n_psteps = rec.shape[0]
+        p.w0_per_path = w0_per_path
+        p.seed = (seed + seg.step_base*0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        steps = np.stack((seg.ds, np.sqrt(np.abs(seg.ds))), axis=1) if n else np.zeros((0, 2))
+        steps_d = _cuda.to_device(steps, dev)
+        rows_d = _cuda.to_device(seg.store_row, dev, dtype=np.int32)
+        rec_d = _cuda.to_device(rec, dev)
+        keep += [steps_d, rows_d, rec_d]
+        p.steps, p.store_row = steps_d.data_ptr(), rows_d.data_ptr()
+        p.params, p.w0 = rec_d.data_ptr(), w0_d.data_ptr()
+        if replay is not None:
+            tabs = replay[k]
+            for name in ('dW', 'dJ', 'dN'):
+                t = tabs.get(name)
+                if t is None:
+                    continue
+                if not isinstance(t, torch.Tensor):
+                    t = _cuda.to_device(
+                        np.asarray(t), dev,
+                        dtype=(np.int64 if name == 'dN' else float))
+                elif not t.is_cuda:
+                    t = t.to(dev)
+                want = torch.int64 if name == 'dN' else torch.float64
+                if t.dtype != want:
+                    t = t.to(want)
+                t = t.contiguous()
+                if t.numel() != n*spec.groups*(spec.ndw if name == 'dW' else spec.nw)*paths:
+                    raise ValueError(
+                        'replay table {} has {} elements, expected steps x '
+                        'lanes x paths = {} x {} x {}'.format(
+                            name, t.numel(), n,
+                            spec.groups*(spec.ndw if name == 'dW' else spec.nw), paths))
+                keep.append(t)
+                setattr(p, name, t.data_ptr())
+        if want_out:
+            p.out = res.out.data_ptr()
+        if res.counter is not None:
+            # the reference re-initialises its diagnostics at every sweep
+            # (info_begin, integration.py:2421, 2588): keep the last sweep's
+            res.counter.zero_()
+            p.counter = res.counter.data_ptr()
+        dn_d = None
+        if dn_sums and spec.jumps:
+            dn_d = _cuda.zeros((max(n, 1),), dev, torch.int64)
+            p.dn_sum = dn_d.data_ptr()
+        if dump and replay is None:
+            d = {'dW': _cuda.empty((n, spec.groups*spec.ndw, paths), dev)}
+            p.dW_dump = d['dW'].data_ptr()
+            if spec.jumps:
+                d['dJ'] = _cuda.empty((n, spec.groups*spec.nw, paths), dev)
+                d['dN'] = _cuda.empty((n, spec.groups*spec.nw, paths), dev, torch.int64)
+                p.dJ_dump, p.dN_dump = d['dJ'].data_ptr(), d['dN'].data_ptr()
+            res.dump.append(d)
+        p.max_blocks = max_blocks
+        seg_stats = None
+        if want_stats:
+            p.centre = centre_d.data_ptr()
+            if payoff is not None:
+                kind, strike, scale = payoff
+                p.payoff_kind = {'call': _lib.PAYOFF_CALL, 'put': _lib.PAYOFF_PUT}[kind]
+                p.payoff_strike, p.payoff_scale = float(strike), float(scale)
+            seg_stats = _cuda.empty((n_rows, gx, _lib.NSTAT), dev)
+            p.stats = seg_stats.data_ptr()
+            plan = _lib.plan(p)
+            if not plan.stats_in_kernel:
+                raise NotImplementedError(
+                    "output='stats' with {} rows x {} components exceeds the "
+                    "in-kernel accumulators: use output='device' and the "
+                    "pmean/pvar/pstd or montecarlo reductions".format(n_rows, gx))
+            ws = _cuda.empty((max(plan.workspace_bytes//8, 1),), dev)
+            keep.append(ws)
+            p.workspace, p.workspace_bytes = ws.data_ptr(), plan.workspace_bytes
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.sdeb_integrate(C.byref(p), _cuda.stream_ptr(dev)))
+        if seg_stats is not None:
+            stats_total = seg_stats if stats_total is None else _merge_stats(stats_total, seg_stats, seg)
+        res.dn_sum.append(dn_d)
+        # the next segment starts again from the initial state (both sweeps
+        # depart from tt[i0]); nothing is carried over.
+    res.stats = stats_total
+    res.dn_sum = [None if d is None else d.cpu().numpy() for d in res.dn_sum]
+    res._keep = keep
+    return res
+
+
+def _merge_stats(a, b, seg):
+    """Rows are disjoint between the backward and forward sweeps: take, row by
+    row, the sweep that stored it."""
+    rows = torch.as_tensor(sorted(set(int(r) for r in seg.store_row if r >= 0)),
+                           device=a.device, dtype=torch.long)
+    out = a.clone()
+    out[rows] = b[rows]
+    return out
+
+
+class resident_stats_run:
+    """A terminal-statistics integration whose tables are already resident in
+    HBM: ``launch(seed)`` only enqueues the fused kernel (+ the fold of the
+    per-block partials).  Used by bench.py for the device-timed number; the
+    public API (SDE.__call__) re-uploads its few KB of tables at every call."""
+
+    def __init__(self, sde, timeline):
+        tt = np.asarray(timeline, dtype=float)
+        target = sde.pace(tt)
+        target = target[(target >= tt[0]) & (target <= tt[-1])]
+        grid = np.unique(np.concatenate((target, tt)))
+        seg, = segments_of(tt, grid, 0)
+        spec, lead = sde._spec()
+        self.dev = dev = _cuda.device(sde.device)
+        self.paths, self.n_steps = sde.paths, seg.n_steps
+        w0 = sde._initial_state(tt[0]).reshape(spec.groups, spec.nw, -1)
+        rec = np.ascontiguousarray(sde._records(spec, seg, lead, False))
+        gx = spec.groups*spec.nx
+        steps = np.stack((seg.ds, np.sqrt(np.abs(seg.ds))), axis=1)
+        self._bufs = dict(
+            steps=_cuda.to_device(steps, dev),
+            rows=_cuda.to_device(seg.store_row, dev, dtype=np.int32),
+            rec=_cuda.to_device(rec, dev),
+            w0=_cuda.to_device(np.ascontiguousarray(w0[..., 0]), dev),
+            centre=_cuda.to_device(sde._stats_centre(w0).reshape(gx), dev),
+            stats=_cuda.empty((tt.size, gx, _lib.NSTAT), dev))
+        p = self.p = _lib.Problem()
+        p.abi_version = _lib.ABI_VERSION
+        p.model, p.ncomp = spec.model, spec.ncomp
+        p.noise = _lib.NOISE_PHILOX
+        p.n_paths, p.path_offset, p.pitch = sde.paths, sde.path_offset, sde.paths
+        p.n_steps, p.n_groups, p.n_rows = seg.n_steps, spec.groups, tt.size
+        p.row0, p.n_psteps = seg.row0, rec.shape[0]
+        b = self._bufs
+        p.steps, p.store_row = b['steps'].data_ptr(), b['rows'].data_ptr()
+        p.params, p.w0 = b['rec'].data_ptr(), b['w0'].data_ptr()
+        p.centre, p.stats = b['centre'].data_ptr(), b['stats'].data_ptr()
+        if sde.payoff is not None:
+            kind, strike, scale = sde.payoff
+            p.payoff_kind = {'call': _lib.PAYOFF_CALL, 'put': _lib.PAYOFF_PUT}[kind]
+            p.payoff_strike, p.payoff_scale = float(strike), float(scale)
+        plan = self.plan = _lib.plan(p)
+        b['ws'] = _cuda.empty((max(plan.workspace_bytes//8, 1),), dev)
+        p.workspace, p.workspace_bytes = b['ws'].data_ptr(), plan.workspace_bytes
+        self.stats = b['stats']
+        self.kernels_per_launch = 2          # integrate + fold_partials
+
+    def launch(self, seed):
+        self.p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib.sdeb_integrate(C.byref(self.p), _cuda.stream_ptr(self.dev)))
+        return self.stats

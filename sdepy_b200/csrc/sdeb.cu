@@ -1,0 +1,679 @@
+// sdeb.cu -- C ABI (include/sdeb.h) over the sm_100a kernels of sde_engine.cuh.
+// Build: see __graft_entry__.build() / sdepy_b200/_build.py
+//   nvcc -shared -Xcompiler -fPIC -gencode arch=compute_100a,code=sm_100a -lineinfo
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sdeb.h"
+#include "sde_engine.cuh"
+
+using namespace sdeb;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                              \
+    do {                                                                            \
+        cudaError_t e_ = (expr);                                                    \
+        if (e_ != cudaSuccess)                                                      \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver \
+                            ? SDEB_ENODEV : SDEB_ECUDA,                             \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+extern "C" int sdeb_abi_version(void) { return SDEB_ABI_VERSION; }
+extern "C" const char* sdeb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int sdeb_device_info(int64_t* sm_count, int64_t* cc_major, int64_t* cc_minor,
+                                int64_t* total_mem_bytes) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (total_mem_bytes) *total_mem_bytes = (int64_t)prop.totalGlobalMem;
+    return SDEB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// model registry (pre-instantiated presets)
+// ---------------------------------------------------------------------------
+struct ModelInfo {
+    const void* fn;
+    int nw, ndw, nx, npc, ncnt, jumps;
+};
+
+template <class M>
+static ModelInfo info_of() {
+    ModelInfo mi;
+    mi.fn = (const void*)&integrate_kernel<M>;
+    mi.nw = M::NW; mi.ndw = M::NDW; mi.nx = M::NX; mi.npc = M::NPC;
+    mi.ncnt = M::NCNT; mi.jumps = M::JUMPS;
+    return mi;
+}
+
+struct JitModule {
+    cudaLibrary_t lib;
+    cudaKernel_t kernel;
+    ModelInfo mi;
+};
+static std::mutex g_jit_mutex;
+static std::map<int64_t, JitModule> g_jit;
+static int64_t g_jit_next = 1;
+
+static bool lookup_model(int64_t model, int64_t n, int64_t jit_handle, ModelInfo& mi) {
+    switch (model) {
+    case SDEB_MODEL_LINEAR:
+        if (n == 1) { mi = info_of<LinearSDE<1, false, false>>(); return true; }
+        if (n == 2) { mi = info_of<LinearSDE<2, false, false>>(); return true; }
+        if (n == 3) { mi = info_of<LinearSDE<3, false, false>>(); return true; }
+        if (n == 4) { mi = info_of<LinearSDE<4, false, false>>(); return true; }
+        return false;
+    case SDEB_MODEL_LINEAR_LOG:
+        if (n == 1) { mi = info_of<LinearSDE<1, true, false>>(); return true; }
+        if (n == 2) { mi = info_of<LinearSDE<2, true, false>>(); return true; }
+        if (n == 3) { mi = info_of<LinearSDE<3, true, false>>(); return true; }
+        if (n == 4) { mi = info_of<LinearSDE<4, true, false>>(); return true; }
+        return false;
+    case SDEB_MODEL_JUMPDIFF:
+        if (n == 1) { mi = info_of<LinearSDE<1, true, true>>(); return true; }
+        if (n == 2) { mi = info_of<LinearSDE<2, true, true>>(); return true; }
+        return false;
+    case SDEB_MODEL_MEANREV:
+        if (n == 1) { mi = info_of<MeanRevertingSDE<1, false>>(); return true; }
+        if (n == 2) { mi = info_of<MeanRevertingSDE<2, false>>(); return true; }
+        if (n == 3) { mi = info_of<MeanRevertingSDE<3, false>>(); return true; }
+        if (n == 4) { mi = info_of<MeanRevertingSDE<4, false>>(); return true; }
+        return false;
+    case SDEB_MODEL_HULL_WHITE:
+        if (n == 1) { mi = info_of<MeanRevertingSDE<1, true>>(); return true; }
+        if (n == 2) { mi = info_of<MeanRevertingSDE<2, true>>(); return true; }
+        if (n == 3) { mi = info_of<MeanRevertingSDE<3, true>>(); return true; }
+        if (n == 4) { mi = info_of<MeanRevertingSDE<4, true>>(); return true; }
+        return false;
+    case SDEB_MODEL_CIR:
+        if (n == 1) { mi = info_of<CoxIngersollRossSDE<1>>(); return true; }
+        if (n == 2) { mi = info_of<CoxIngersollRossSDE<2>>(); return true; }
+        return false;
+    case SDEB_MODEL_HESTON:
+        if (n == 1) { mi = info_of<HestonSDE<1, false>>(); return true; }
+        if (n == 2) { mi = info_of<HestonSDE<2, false>>(); return true; }
+        return false;
+    case SDEB_MODEL_HESTON_FULL:
+        if (n == 1) { mi = info_of<HestonSDE<1, true>>(); return true; }
+        if (n == 2) { mi = info_of<HestonSDE<2, true>>(); return true; }
+        return false;
+    case SDEB_MODEL_JIT: {
+        std::lock_guard<std::mutex> lock(g_jit_mutex);
+        auto it = g_jit.find(jit_handle);
+        if (it == g_jit.end()) return false;
+        mi = it->second.mi;
+        return true;
+    }
+    default:
+        return false;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------
+static const int kThreads = 256;
+static const int64_t kMaxStatsSmem = 96 * 1024;   // accumulators kept in smem up to here
+
+static int64_t smem_bytes(const ModelInfo& mi, const sdeb_problem* p, bool stats_in_kernel) {
+    int64_t nch = mi.ndw > 1 ? (int64_t)mi.ndw * (mi.ndw + 1) / 2 : 0;
+    int64_t npt = mi.npc + nch;
+    int64_t d = TAB_DOUBLES + 2 * STEP_CHUNK + (int64_t)STEP_CHUNK * npt + 8 * NSTAT * mi.nx;
+    if (stats_in_kernel) d += p->n_rows * p->n_groups * mi.nx * NSTAT;
+    return d * 8 + STEP_CHUNK * 4;
+}
+
+static int plan_impl(const sdeb_problem* p, sdeb_plan_t* plan, ModelInfo& mi, bool need_device) {
+    if (!p || !plan) return fail(SDEB_EINVAL, "null problem/plan");
+    if (p->abi_version != SDEB_ABI_VERSION)
+        return fail(SDEB_EINVAL, "sdeb_problem.abi_version mismatch");
+    if (!lookup_model(p->model, p->ncomp, p->jit_handle, mi)) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "model %lld with ncomp=%lld is not pre-instantiated "
+                 "(use the JIT path)", (long long)p->model, (long long)p->ncomp);
+        return fail(SDEB_EINVAL, buf);
+    }
+    if (p->n_paths < 0 || p->n_steps < 0 || p->n_groups < 1 || p->n_rows < 0 ||
+        p->pitch < p->n_paths)
+        return fail(SDEB_EINVAL, "inconsistent sizes (n_paths/n_steps/n_groups/n_rows/pitch)");
+    if (p->n_groups >= (1 << 24)) return fail(SDEB_EINVAL, "n_groups must be < 2^24");
+    if (p->n_psteps != 1 && p->n_psteps != p->n_steps)
+        return fail(SDEB_EINVAL, "n_psteps must be 1 or n_steps");
+    memset(plan, 0, sizeof *plan);
+    plan->nw = mi.nw; plan->ndw = mi.ndw; plan->nx = mi.nx; plan->npc = mi.npc;
+    plan->npt = mi.npc + (mi.ndw > 1 ? (int64_t)mi.ndw * (mi.ndw + 1) / 2 : 0);
+    plan->ncnt = mi.ncnt; plan->jumps = mi.jumps;
+    plan->threads = kThreads;
+    int64_t acc = p->n_rows * p->n_groups * mi.nx * NSTAT * 8;
+    plan->stats_in_kernel = (acc <= kMaxStatsSmem) ? 1 : 0;
+    bool sik = p->stats != NULL && plan->stats_in_kernel;
+    plan->smem_bytes = smem_bytes(mi, p, sik);
+    int64_t tiles = ((p->n_paths + kThreads - 1) / kThreads) * p->n_groups;
+    int sm = 148, occ = 2;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) {
+        cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+        if (plan->smem_bytes > 48 * 1024)
+            cudaFuncSetAttribute(mi.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)plan->smem_bytes);
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, mi.fn, kThreads,
+                                                          (size_t)plan->smem_bytes) == cudaSuccess && o > 0)
+            occ = o;
+    } else {
+        cudaGetLastError();
+        if (need_device) return fail(SDEB_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    }
+    int64_t blocks = (int64_t)sm * occ;          // persistent grid: resident CTAs only
+    if (p->max_blocks > 0 && blocks > p->max_blocks) blocks = p->max_blocks;
+    if (blocks > tiles) blocks = tiles;
+    if (blocks < 1) blocks = 1;
+    plan->blocks = blocks;
+    plan->workspace_bytes = blocks * acc;
+    return SDEB_OK;
+}
+
+extern "C" int sdeb_plan(const sdeb_problem* p, sdeb_plan_t* plan) {
+    ModelInfo mi;
+    return plan_impl(p, plan, mi, false);
+}
+
+// fold per-block statistics partials in block order (deterministic)
+__global__ void fold_partials_kernel(const double* partials, int64_t n_blocks, int64_t len,
+                                     double* stats) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    int k = (int)(i % NSTAT);
+    double acc = partials[i];
+    for (int64_t b = 1; b < n_blocks; ++b) {
+        double o = partials[b * len + i];
+        acc = (k == 4) ? fmin(acc, o) : (k == 5) ? fmax(acc, o) : acc + o;
+    }
+    stats[i] = acc;
+}
+
+extern "C" int sdeb_integrate(const sdeb_problem* p, void* stream_) {
+    ModelInfo mi;
+    sdeb_plan_t plan;
+    int rc = plan_impl(p, &plan, mi, true);
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (p->n_paths == 0) return SDEB_OK;
+    if (!p->steps && p->n_steps > 0) return fail(SDEB_EINVAL, "steps table is NULL");
+    if (!p->params || !p->w0) return fail(SDEB_EINVAL, "params / w0 is NULL");
+    if (p->noise == SDEB_NOISE_REPLAY) {
+        if (!p->dW) return fail(SDEB_EINVAL, "replay mode needs dW");
+        if (mi.jumps && !p->dJ) return fail(SDEB_EINVAL, "replay mode needs dJ for jump models");
+    }
+    if (p->stats) {
+        if (!plan.stats_in_kernel)
+            return fail(SDEB_EINVAL, "statistics accumulators exceed shared memory: "
+                        "store the rows and use sdeb_moments");
+        if (!p->workspace || p->workspace_bytes < plan.workspace_bytes)
+            return fail(SDEB_EINVAL, "workspace too small (see sdeb_plan)");
+        if (!p->centre) return fail(SDEB_EINVAL, "stats need a centre vector");
+    }
+    KArgs a;
+    memset(&a, 0, sizeof a);
+    a.n_paths = p->n_paths; a.path_offset = p->path_offset; a.pitch = p->pitch;
+    a.n_steps = (int)p->n_steps; a.n_groups = (int)p->n_groups; a.n_rows = (int)p->n_rows;
+    a.row0 = (int)p->row0; a.n_psteps = (int)p->n_psteps; a.w0_per_path = (int)p->w0_per_path;
+    a.noise = (int)p->noise;
+    a.payoff_kind = (int)p->payoff_kind; a.payoff_strike = p->payoff_strike;
+    a.payoff_scale = p->payoff_scale;
+    a.seed = p->seed;
+    a.steps = p->steps; a.store_row = p->store_row; a.params = p->params; a.w0 = p->w0;
+    a.dW = p->dW; a.dJ = p->dJ; a.dN = (const i64*)p->dN;
+    a.out = p->out; a.partials = p->stats ? (double*)p->workspace : NULL;
+    a.centre = p->centre; a.counter = (i64*)p->counter; a.dn_sum = (i64*)p->dn_sum;
+    a.dW_dump = p->dW_dump; a.dJ_dump = p->dJ_dump; a.dN_dump = (i64*)p->dN_dump;
+
+    void* args[] = {&a};
+    CUDA_TRY(cudaLaunchKernel(mi.fn, dim3((unsigned)plan.blocks), dim3(kThreads), args,
+                              (size_t)plan.smem_bytes, stream));
+    if (p->stats) {
+        int64_t len = p->n_rows * p->n_groups * mi.nx * NSTAT;
+        fold_partials_kernel<<<(unsigned)((len + 127) / 128), 128, 0, stream>>>(
+            (const double*)p->workspace, plan.blocks, len, p->stats);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return SDEB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// across-path statistics of stored rows
+// ---------------------------------------------------------------------------
+static const int kMomBlocks = 296;   // per row: 2 x 148 SMs
+
+__global__ void __launch_bounds__(256)
+moments_kernel(const double* x, int64_t n_paths, int64_t pitch, const double* centre,
+               double* partials) {
+    const int row = blockIdx.y;
+    const double c = centre ? centre[row] : 0.0;
+    const double* xr = x + (int64_t)row * pitch;
+    double st[NSTAT];
+    st[0] = st[1] = st[2] = st[3] = st[6] = st[7] = 0.0;
+    st[4] = __longlong_as_double(0x7FF0000000000000LL);
+    st[5] = __longlong_as_double(0xFFF0000000000000LL);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_paths;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double v = xr[i];
+        double d = v - c, d2 = d * d;
+        st[0] += d; st[1] += d2; st[2] += d2 * d; st[3] += d2 * d2;
+        st[4] = fmin(st[4], v); st[5] = fmax(st[5], v);
+    }
+    __shared__ double s_warp[8][NSTAT];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < NSTAT; ++k) {
+            double o = __shfl_down_sync(0xffffffffu, st[k], off);
+            st[k] = (k == 4) ? fmin(st[k], o) : (k == 5) ? fmax(st[k], o) : st[k] + o;
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NSTAT; ++k) s_warp[warp][k] = st[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < NSTAT) {
+        int k = threadIdx.x;
+        double acc = s_warp[0][k];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            double o = s_warp[w][k];
+            acc = (k == 4) ? fmin(acc, o) : (k == 5) ? fmax(acc, o) : acc + o;
+        }
+        // layout [block][row][NSTAT] so that fold_partials_kernel applies
+        partials[((int64_t)blockIdx.x * gridDim.y + row) * NSTAT + k] = acc;
+    }
+}
+
+extern "C" int64_t sdeb_moments_workspace(int64_t n_rows) {
+    return (int64_t)kMomBlocks * n_rows * NSTAT * 8;
+}
+
+extern "C" int sdeb_moments(const double* x, int64_t n_rows, int64_t n_paths, int64_t pitch,
+                            const double* centre, double* stats, void* workspace,
+                            int64_t workspace_bytes, void* stream_) {
+    if (!x || !stats || n_rows < 1 || n_paths < 1 || pitch < n_paths)
+        return fail(SDEB_EINVAL, "sdeb_moments: bad arguments");
+    if (n_rows > 65535) return fail(SDEB_EINVAL, "sdeb_moments: n_rows > 65535 (chunk the rows)");
+    if (!workspace || workspace_bytes < sdeb_moments_workspace(n_rows))
+        return fail(SDEB_EINVAL, "sdeb_moments: workspace too small");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int64_t need = (n_paths + 255) / 256;
+    int blocks = (int)(need < kMomBlocks ? need : kMomBlocks);
+    moments_kernel<<<dim3(blocks, (unsigned)n_rows), 256, 0, stream>>>(
+        x, n_paths, pitch, centre, (double*)workspace);
+    CUDA_TRY(cudaGetLastError());
+    int64_t len = n_rows * NSTAT;
+    fold_partials_kernel<<<(unsigned)((len + 127) / 128), 128, 0, stream>>>(
+        (const double*)workspace, blocks, len, stats);
+    CUDA_TRY(cudaGetLastError());
+    return SDEB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// histogram with numpy.histogram bin semantics
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+histogram_kernel(const double* x, int64_t n, const double* edges, int nbins, int uniform,
+                 unsigned long long* counts, unsigned long long* outside) {
+    extern __shared__ double sh[];
+    double* s_edges = sh;                                   // nbins + 1
+    unsigned int* s_cnt = (unsigned int*)(sh + nbins + 1);  // nbins + 1 (last: outside)
+    for (int i = threadIdx.x; i <= nbins; i += blockDim.x) { s_edges[i] = edges[i]; s_cnt[i] = 0; }
+    __syncthreads();
+    const double lo = s_edges[0], hi = s_edges[nbins];
+    const double scale = nbins / (hi - lo);
+    // each block handles a contiguous span so that 32-bit bin counters cannot overflow
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double v = x[i];
+        int idx;
+        if (!(v >= lo && v <= hi)) {
+            idx = nbins;                                    // outside (or NaN)
+        } else {
+            if (uniform) {
+                idx = (int)((v - lo) * scale);
+                idx = idx < 0 ? 0 : (idx > nbins - 1 ? nbins - 1 : idx);
+            } else {
+                int a = 0, b = nbins;                       // largest idx with edges[idx] <= v
+                while (b - a > 1) { int m = (a + b) >> 1; if (s_edges[m] <= v) a = m; else b = m; }
+                idx = a;
+            }
+            while (idx > 0 && v < s_edges[idx]) --idx;
+            while (idx < nbins - 1 && v >= s_edges[idx + 1]) ++idx;
+        }
+        atomicAdd(&s_cnt[idx], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= nbins; i += blockDim.x) {
+        unsigned int c = s_cnt[i];
+        if (c) atomicAdd(i < nbins ? &counts[i] : outside, (unsigned long long)c);
+    }
+}
+
+extern "C" int sdeb_histogram(const double* x, int64_t n, const double* edges, int64_t nbins,
+                              int64_t uniform_edges, int64_t* counts, int64_t* outside,
+                              void* stream_) {
+    if (!x || !edges || !counts || !outside || nbins < 1 || n < 0)
+        return fail(SDEB_EINVAL, "sdeb_histogram: bad arguments");
+    if (nbins > 4000) return fail(SDEB_EINVAL, "sdeb_histogram: at most 4000 bins");
+    if (n == 0) return SDEB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int64_t need = (n + 255) / 256;
+    // >= n / 2^31 blocks keeps the 32-bit shared counters from overflowing
+    int blocks = (int)(need < 1184 ? need : 1184);
+    size_t smem = (size_t)(nbins + 1) * 12;
+    histogram_kernel<<<blocks, 256, smem, stream>>>(x, n, edges, (int)nbins, (int)uniform_edges,
+                                                    (unsigned long long*)counts,
+                                                    (unsigned long long*)outside);
+    CUDA_TRY(cudaGetLastError());
+    return SDEB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// standalone source draws
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+draw_wiener_kernel(double* out, int n_groups, int ndw, int64_t n_paths, int64_t pitch,
+                   int64_t path_offset, u64 seed, u32 step, double sq, const double* chol) {
+    __shared__ double tab[TAB_DOUBLES];
+    fill_tables(tab);
+    __syncthreads();
+    const int64_t path = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (path >= n_paths) return;
+    const u64 gpath = (u64)(path_offset + path);
+    Rng rng;
+    rng.k0 = (u32)seed; rng.k1 = (u32)(seed >> 32);
+    rng.c_x = (u32)gpath; rng.c_y = ((u32)(gpath >> 32) & 0xFFu) | ((u32)g << 8);
+    rng.step = step;
+    double z[34];
+    for (int b = 0; b < (ndw + 1) / 2; ++b) {
+        U4 w = rng.block((u32)b);
+        normal_pair(w, tab, 1.0, z[2*b], z[2*b + 1]);
+    }
+    for (int r = ndw - 1; r >= 0; --r) {
+        double acc = z[r];
+        if (chol && r > 0) {
+            acc = 0.0;
+            for (int c = 0; c <= r; ++c) acc = fma(chol[r*(r+1)/2 + c], z[c], acc);
+        }
+        out[((int64_t)g * ndw + r) * pitch + path] = xmul(acc, sq);
+        z[r] = acc;
+    }
+}
+
+extern "C" int sdeb_draw_wiener(double* out, int64_t n_groups, int64_t ndw, int64_t n_paths,
+                                int64_t pitch, int64_t path_offset, uint64_t seed, int64_t step,
+                                double sqrt_abs_dt, const double* chol, void* stream_) {
+    if (!out || n_groups < 1 || n_groups > 65535 || ndw < 1 || ndw > 32 || n_paths < 1 ||
+        pitch < n_paths)
+        return fail(SDEB_EINVAL, "sdeb_draw_wiener: bad arguments (ndw <= 32, n_groups <= 65535)");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    dim3 grid((unsigned)((n_paths + 255) / 256), (unsigned)n_groups);
+    draw_wiener_kernel<<<grid, 256, 0, stream>>>(out, (int)n_groups, (int)ndw, n_paths, pitch,
+                                                 path_offset, seed, (u32)step, sqrt_abs_dt, chol);
+    CUDA_TRY(cudaGetLastError());
+    return SDEB_OK;
+}
+
+__global__ void __launch_bounds__(256)
+draw_cpoisson_kernel(double* dj, i64* dn, int64_t n_paths, int64_t pitch, int64_t path_offset,
+                     u64 seed, u32 step, double lamdt, double explam, int sign, int law,
+                     double a, double b, double pa) {
+    __shared__ double tab[TAB_DOUBLES];
+    fill_tables(tab);
+    __syncthreads();
+    const int64_t path = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (path >= n_paths) return;
+    const u64 gpath = (u64)(path_offset + path);
+    Rng rng;
+    rng.k0 = (u32)seed; rng.k1 = (u32)(seed >> 32);
+    rng.c_x = (u32)gpath; rng.c_y = ((u32)(gpath >> 32) & 0xFFu) | ((u32)g << 8);
+    rng.step = step;
+    U4 w = rng.block((u32)STREAM_POISSON);
+    int k = poisson_inv(u01(w.x, w.y), lamdt, explam);
+    double sum = 0.0;
+    for (int j = 0; j < k; ++j) {
+        U4 wj = rng.block((u32)(STREAM_JUMP + j));
+        double yj = jump_size(wj, tab, law, a, b, pa);
+        sum = (j == 0) ? yj : sum + yj;
+    }
+    if (dj) dj[(int64_t)g * pitch + path] = sign * sum;
+    if (dn) dn[(int64_t)g * pitch + path] = (i64)sign * k;
+}
+
+extern "C" int sdeb_draw_cpoisson(double* dj, int64_t* dn, int64_t n_lanes, int64_t n_paths,
+                                  int64_t pitch, int64_t path_offset, uint64_t seed,
+                                  int64_t step, double lam_abs_dt, int64_t sign, int64_t law,
+                                  double a, double b, double pa, void* stream_) {
+    if ((!dj && !dn) || n_lanes < 1 || n_lanes > 65535 || n_paths < 1 || pitch < n_paths ||
+        lam_abs_dt < 0)
+        return fail(SDEB_EINVAL, "sdeb_draw_cpoisson: bad arguments");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    dim3 grid((unsigned)((n_paths + 255) / 256), (unsigned)n_lanes);
+    draw_cpoisson_kernel<<<grid, 256, 0, stream>>>(dj, (i64*)dn, n_paths, pitch, path_offset, seed,
+                                                   (u32)step, lam_abs_dt, exp(-lam_abs_dt),
+                                                   (int)sign, (int)law, a, b, pa);
+    CUDA_TRY(cudaGetLastError());
+    return SDEB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// self tests / measurement
+// ---------------------------------------------------------------------------
+__global__ void test_normals_kernel(u64 seed, int64_t n, double* zf, double* zl) {
+    __shared__ double tab[TAB_DOUBLES];
+    fill_tables(tab);
+    __syncthreads();
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Rng rng;
+    rng.k0 = (u32)seed; rng.k1 = (u32)(seed >> 32);
+    rng.c_x = (u32)i; rng.c_y = (u32)(i >> 32); rng.step = 0;
+    U4 w = rng.block(0);
+    if (i < 64) {   // force the extreme corners of the bit space through both maps
+        if (i & 1) w.x = 0;             // e = 33: deepest tail
+        if (i & 2) { w.y = 0xFFFFFFFFu; w.z = 0xFFFFFFFFu; }   // m -> 2
+        if (i & 4) { w.y = 0; w.z = 0; }                       // m = 1
+        if (i & 8) w.x = 0x80000000u;   // e = 1
+        if (i & 16) w.w = 0xFFFFFFFFu;
+        if (i & 32) w.w = 0;
+    }
+    normal_pair(w, tab, 1.0, zf[2*i], zf[2*i + 1]);
+    normal_pair_libdevice(w, zl[2*i], zl[2*i + 1]);
+}
+
+extern "C" int sdeb_test_normals(uint64_t seed, int64_t n, double* z_fast, double* z_libdevice,
+                                 void* stream_) {
+    if (!z_fast || !z_libdevice || n < 1) return fail(SDEB_EINVAL, "sdeb_test_normals: bad arguments");
+    test_normals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+        seed, n, z_fast, z_libdevice);
+    CUDA_TRY(cudaGetLastError());
+    return SDEB_OK;
+}
+
+// host-side Philox (same code path as the device one) for known-answer tests
+extern "C" int sdeb_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+    return SDEB_OK;
+}
+
+__global__ void __launch_bounds__(256)
+fp64_peak_kernel(int64_t iters, double* sink) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int64_t i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) sink[0] = s;
+}
+
+extern "C" int sdeb_fp64_peak(int64_t iters, double* dfma_per_second, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int dev = 0, sm = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+    double* sink = NULL;
+    CUDA_TRY(cudaMalloc(&sink, 8));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    int blocks = sm * 8;
+    fp64_peak_kernel<<<blocks, 256, 0, stream>>>(iters / 8 + 1, sink);   // warm-up
+    CUDA_TRY(cudaEventRecord(e0, stream));
+    fp64_peak_kernel<<<blocks, 256, 0, stream>>>(iters, sink);
+    CUDA_TRY(cudaEventRecord(e1, stream));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    if (dfma_per_second) *dfma_per_second = (double)blocks * 256.0 * 8.0 * (double)iters / (ms * 1e-3);
+    return SDEB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// NVRTC JIT (libnvrtc is dlopen'ed on first use; module loading goes through
+// the runtime's cudaLibrary API so that libcuda is never a link dependency)
+// ---------------------------------------------------------------------------
+typedef int nvrtcResult_t;
+typedef struct _nvrtcProgram* nvrtcProgram_t;
+struct NvrtcApi {
+    void* h;
+    nvrtcResult_t (*CreateProgram)(nvrtcProgram_t*, const char*, const char*, int,
+                                   const char* const*, const char* const*);
+    nvrtcResult_t (*CompileProgram)(nvrtcProgram_t, int, const char* const*);
+    nvrtcResult_t (*GetProgramLogSize)(nvrtcProgram_t, size_t*);
+    nvrtcResult_t (*GetProgramLog)(nvrtcProgram_t, char*);
+    nvrtcResult_t (*GetCUBINSize)(nvrtcProgram_t, size_t*);
+    nvrtcResult_t (*GetCUBIN)(nvrtcProgram_t, char*);
+    nvrtcResult_t (*DestroyProgram)(nvrtcProgram_t*);
+    const char* (*GetErrorString)(nvrtcResult_t);
+};
+static NvrtcApi g_nvrtc;
+
+static int load_nvrtc() {
+    if (g_nvrtc.h) return SDEB_OK;
+    const char* names[] = {"libnvrtc.so.12", "libnvrtc.so",
+                           "/usr/local/cuda/lib64/libnvrtc.so.12", NULL};
+    void* h = NULL;
+    for (int i = 0; names[i] && !h; ++i) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(SDEB_EJIT, std::string("cannot dlopen libnvrtc: ") + dlerror());
+#define NVRTC_SYM(field, name)                                              \
+    *(void**)(&g_nvrtc.field) = dlsym(h, name);                             \
+    if (!g_nvrtc.field) return fail(SDEB_EJIT, "libnvrtc lacks " name);
+    NVRTC_SYM(CreateProgram, "nvrtcCreateProgram")
+    NVRTC_SYM(CompileProgram, "nvrtcCompileProgram")
+    NVRTC_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+    NVRTC_SYM(GetProgramLog, "nvrtcGetProgramLog")
+    NVRTC_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+    NVRTC_SYM(GetCUBIN, "nvrtcGetCUBIN")
+    NVRTC_SYM(DestroyProgram, "nvrtcDestroyProgram")
+    NVRTC_SYM(GetErrorString, "nvrtcGetErrorString")
+#undef NVRTC_SYM
+    g_nvrtc.h = h;
+    return SDEB_OK;
+}
+
+// `source` = engine header + model definition + an
+//   extern "C" __global__ void sdeb_jit_entry(const sdeb::KArgs a)
+// wrapper plus  extern "C" __constant__ int sdeb_jit_dims[6] = {NW,NDW,NX,NPC,NCNT,JUMPS};
+// (the Python side generates all of it, sdepy_b200/_jit.py); `model_type` is only
+// used as the NVRTC program name.
+extern "C" int sdeb_jit_compile(const char* source, const char* model_type, int64_t* handle,
+                                char* log, int64_t log_bytes) {
+    if (!source || !handle) return fail(SDEB_EINVAL, "sdeb_jit_compile: null argument");
+    if (log && log_bytes > 0) log[0] = 0;
+    int rc = load_nvrtc();
+    if (rc) return rc;
+    nvrtcProgram_t prog;
+    nvrtcResult_t r = g_nvrtc.CreateProgram(&prog, source, model_type ? model_type : "sdeb_jit.cu",
+                                            0, NULL, NULL);
+    if (r) return fail(SDEB_EJIT, std::string("nvrtcCreateProgram: ") + g_nvrtc.GetErrorString(r));
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17",
+                          "-default-device"};
+    r = g_nvrtc.CompileProgram(prog, 3, opts);
+    size_t lsz = 0;
+    g_nvrtc.GetProgramLogSize(prog, &lsz);
+    std::string plog(lsz, 0);
+    if (lsz > 1) g_nvrtc.GetProgramLog(prog, &plog[0]);
+    if (log && log_bytes > 0) { strncpy(log, plog.c_str(), (size_t)log_bytes - 1); log[log_bytes - 1] = 0; }
+    if (r) {
+        g_nvrtc.DestroyProgram(&prog);
+        return fail(SDEB_EJIT, std::string("nvrtcCompileProgram: ") + g_nvrtc.GetErrorString(r) +
+                    "\n" + plog);
+    }
+    size_t csz = 0;
+    g_nvrtc.GetCUBINSize(prog, &csz);
+    std::vector<char> cubin(csz);
+    g_nvrtc.GetCUBIN(prog, cubin.data());
+    g_nvrtc.DestroyProgram(&prog);
+
+    JitModule jm;
+    CUDA_TRY(cudaLibraryLoadData(&jm.lib, cubin.data(), NULL, NULL, 0, NULL, NULL, 0));
+    CUDA_TRY(cudaLibraryGetKernel(&jm.kernel, jm.lib, "sdeb_jit_entry"));
+    void* dptr = NULL;
+    size_t dbytes = 0;
+    CUDA_TRY(cudaLibraryGetGlobal(&dptr, &dbytes, jm.lib, "sdeb_jit_dims"));
+    int dims[6];
+    if (dbytes < sizeof dims) return fail(SDEB_EJIT, "sdeb_jit_dims has the wrong size");
+    CUDA_TRY(cudaMemcpy(dims, dptr, sizeof dims, cudaMemcpyDeviceToHost));
+    jm.mi.fn = (const void*)jm.kernel;
+    jm.mi.nw = dims[0]; jm.mi.ndw = dims[1]; jm.mi.nx = dims[2]; jm.mi.npc = dims[3];
+    jm.mi.ncnt = dims[4]; jm.mi.jumps = dims[5];
+    std::lock_guard<std::mutex> lock(g_jit_mutex);
+    *handle = g_jit_next++;
+    g_jit[*handle] = jm;
+    return SDEB_OK;
+}
+
+extern "C" int sdeb_jit_release(int64_t handle) {
+    std::lock_guard<std::mutex> lock(g_jit_mutex);
+    auto it = g_jit.find(handle);
+    if (it == g_jit.end()) return fail(SDEB_EINVAL, "sdeb_jit_release: unknown handle");
+    cudaLibraryUnload(it->second.lib);
+    g_jit.erase(it);
+    return SDEB_OK;
+}

@@ -1,0 +1,914 @@
+"""
+Containers, stochasticity sources and Monte Carlo statistics -- the host side
+mirror of ``sdepy/infrastructure.py`` for the hot path only.
+
+* ``process`` : host ``ndarray`` subclass ``(N,)+vshape+(paths,)`` with a
+  timeline (reference ``infrastructure.py:272-456, 861-889``).
+* ``device_process`` : the same container resident in HBM; across-path
+  reductions run as CUDA kernels (``sdeb_moments``).
+* ``wiener_source / poisson_source / cpoisson_source`` : descriptors of the
+  in-kernel Philox draws (reference ``1388-1560, 1566-1633, 1881-2040``); they
+  also obey the reference's source protocol ``dz(t, dt)`` by launching a draw
+  kernel.  ``replay_source`` feeds pre-drawn increments (replay mode).
+* ``montecarlo`` : cumulated moments + histograms (reference ``2718-3312``)
+  computed on the device.
+"""
+import inspect
+
+import numpy as np
+import torch
+
+from . import _cuda, _lib
+
+# --------------------------------------------------------------------------
+# default generator: only used to derive Philox seeds (reference:
+# infrastructure.py:26-51)
+# --------------------------------------------------------------------------
+default_rng = np.random.default_rng()
+
+
+def _get_default_rng():
+    return default_rng
+
+
+def _seed_from(rng):
+    """64-bit Philox key drawn from a numpy Generator / RandomState."""
+    if isinstance(rng, (int, np.integer, list, np.ndarray)):
+        # reference infrastructure.py:1344-1348
+        raise TypeError('`rng` must be an instance of a random number '
+                        'generator, not {}.'.format(type(rng)))
+    rng = default_rng if rng is None else rng
+    if hasattr(rng, 'integers'):
+        return int(rng.integers(0, 2**63 - 1, dtype=np.int64))
+    if hasattr(rng, 'randint'):
+        return (int(rng.randint(0, 2**31 - 1)) << 31) | int(rng.randint(0, 2**31 - 1))
+    raise TypeError('`rng` must be a numpy.random Generator or RandomState, '
+                    'not {}'.format(type(rng)))
+
+
+def _splitmix64(x):
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = x
+    z = ((z ^ (z >> 30))*0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27))*0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
+def _shape_setup(shape):
+    return (shape,) if isinstance(shape, (int, np.integer)) else tuple(shape)
+
+
+def _const_param_setup(z):
+    return z if z is None else np.asarray(z)
+
+
+def _variable_param_setup(z):
+    """Reference infrastructure.py:64-108: arrays stay arrays, callables are
+    probed once at t=1. to learn their shape and wrapped in asarray."""
+    if z is None or isinstance(z, process):
+        return z
+    if callable(z):
+        try:
+            shape = np.asarray(z(1.)).shape
+        except Exception:
+            shape = None
+
+        def wrapped(s, _z=z):
+            return np.asarray(_z(s))
+        wrapped.shape = shape
+        return wrapped
+    return np.asarray(z)
+
+
+def _param_shape(z):
+    if z is None:
+        return None
+    if isinstance(z, process):
+        return z.vshape + (z.paths,)
+    return z.shape
+
+
+def _rho_to_corr(rho):
+    """Reference infrastructure.py:128-150."""
+    if rho is None:
+        return None
+    rho = np.asarray(rho)
+    n = rho.size
+    if rho.shape not in {(), (n,), (n, 1)}:
+        raise ValueError(
+            'correlation ``rho`` should be a vector, possibly with a trailing '
+            '1-dimensional axis matching the paths axis, not an array with '
+            'shape {}'.format(rho.shape))
+    if n == 1:
+        r = rho.reshape(())
+        return np.array(((1, r), (r, 1)))
+    r = rho.reshape(n)
+    eye, dg = np.eye(n), np.diag(r)
+    return np.block([[eye, dg], [dg, eye]])
+
+
+def _corr_matrix(corr, rho):
+    """Reference infrastructure.py:153-206: ``corr`` overrides ``rho``; either
+    may be time-dependent.  Returns None, an array, or a callable."""
+    if corr is None and rho is None:
+        return None
+    if corr is not None:
+        corr = _variable_param_setup(corr)
+        cs = _param_shape(corr)
+        if cs is not None and (len(cs) not in (2, 3) or cs[0] != cs[1] or
+                               (len(cs) == 3 and cs[2] != 1)):
+            raise ValueError(
+                'the correlation matrix ``corr`` should be square, possibly '
+                'with a trailing 1-dimensional axis matching the paths axis, '
+                'not an array with shape {}'.format(cs))
+        return corr
+    rho = _variable_param_setup(rho)
+    rs = _param_shape(rho)
+    if rs is not None and (len(rs) > 2 or (len(rs) == 2 and rs[1] != 1)):
+        raise ValueError(
+            'correlation ``rho`` should be a vector, possibly with a trailing '
+            '1-dimensional axis matching the paths axis, not an array with '
+            'shape {}'.format(rs))
+    if callable(rho):
+        def corr_t(t, _rho=rho):
+            return _rho_to_corr(_rho(t))
+        corr_t.shape = (None if rs is None else (2, 2) if rs == () else
+                        (2*rs[0], 2*rs[0]))
+        return corr_t
+    return _rho_to_corr(rho)
+
+
+def _check_source(src, paths, vshape):
+    """Reference infrastructure.py:209-232."""
+    if callable(src) and hasattr(src, 'paths') and hasattr(src, 'vshape'):
+        ok = (src.paths == paths)
+        try:
+            np.broadcast_to(np.empty(src.vshape), vshape)
+        except ValueError:
+            ok = False
+        if not ok:
+            raise ValueError(
+                'invalid stochasticity source: expecting source paths={} and '
+                'vshape broadcastable to {}, but paths={}, vshape={} were '
+                'found'.format(paths, vshape, src.paths, src.vshape))
+        return
+    raise ValueError(
+        "stochasticity source of type '{}', not compliant with the source "
+        'protocol (should be callable with properly defined paths and vshape '
+        'attributes)'.format(type(src).__name__))
+
+
+def _source_setup(dz, source_type, paths, vshape, **args):
+    """Reference infrastructure.py:235-243: None -> default class, a class ->
+    instantiate, an instance -> validate and use as is."""
+    if dz is None:
+        return source_type(paths=paths, vshape=vshape, **args)
+    if inspect.isclass(dz):
+        return dz(paths=paths, vshape=vshape, **args)
+    _check_source(dz, paths, vshape)
+    return dz
+
+
+_empty = inspect.Signature.empty
+
+
+def _signature(f):
+    return [(k, p.default) for k, p in inspect.signature(f).parameters.items()]
+
+
+# --------------------------------------------------------------------------
+# process (host) and device_process (HBM)
+# --------------------------------------------------------------------------
+
+class process(np.ndarray):
+    """Host container of a realised process: ``x[i]`` are the values at time
+    ``t[i]``, shaped ``vshape + (paths,)`` (reference infrastructure.py:
+    423-456).  Only construction, interpolation-as-source and the
+    across-path summaries are provided; everything else is plain ndarray."""
+
+    __array_priority__ = 1.0
+    interp_kind = 'linear'
+
+    def __new__(cls, t=0., *, x=None, v=None, c=None, dtype=None):
+        t = np.asarray(t)
+        if t.ndim > 1 or t.size == 0:
+            raise ValueError('the shape of a process timeline should be () '
+                             'or (n,), not {}'.format(t.shape))
+        t = t.reshape(-1)
+        if sum(z is not None for z in (x, v, c)) != 1:
+            raise ValueError('when creating a process instance, one and only '
+                             'one of x or v or c should be provided')
+        if x is not None:
+            x = np.asarray(x, dtype=dtype)
+        elif v is not None:
+            x = np.asarray(v, dtype=dtype)[..., np.newaxis]
+        else:
+            c = np.asarray(c, dtype=dtype)
+            x = np.empty(t.shape + c.shape + (1,), dtype=dtype)
+            x[...] = c[np.newaxis, ..., np.newaxis]
+        if t.shape != x.shape[:1]:
+            raise ValueError('process could not be created from timeline t '
+                             'shaped {} and body shaped {}'
+                             .format(t.shape, x.shape))
+        obj = x.view(cls)
+        obj.t = t
+        return obj
+
+    def __array_finalize__(self, obj):
+        t = getattr(obj, 't', None)
+        self.t = t if (t is not None and t.shape == self.shape[:1]) else None
+
+    def __array_wrap__(self, out, context=None, return_scalar=False):
+        if context is None or out.shape[:1] != self.shape[:1]:
+            return np.asarray(out)
+        res = np.asarray(out).view(type(self))
+        res.t = self.t
+        return res
+
+    @property
+    def x(self):
+        return self.view(np.ndarray)
+
+    @property
+    def paths(self):
+        return self.shape[-1]
+
+    @property
+    def vshape(self):
+        return self.shape[1:-1]
+
+    def interp(self, *, kind=None):
+        """Callable ``f(s)`` interpolating the values in time (reference
+        infrastructure.py:544-613)."""
+        import scipy.interpolate
+        kind = self.interp_kind if kind is None else kind
+        t, x = self.t, self.x
+        if t.size == 1:
+            def f(s):
+                return np.broadcast_to(x[0], np.asarray(s).shape + x.shape[1:]).copy()
+            return f
+        g = scipy.interpolate.interp1d(
+            t, x, axis=0, kind=kind, assume_sorted=True, copy=False,
+            bounds_error=False, fill_value=(x[0], x[-1]))
+        return lambda s: g(s).astype(x.dtype, copy=False)
+
+    def __call__(self, s, ds=None, *, kind=None):
+        """``p(s)`` values at ``s``; ``p(s, ds)`` increments -- which makes a
+        process a valid stochasticity source (reference infrastructure.py:
+        615-633)."""
+        f = self.interp(kind=kind)
+        s = np.asarray(s)
+        if ds is None:
+            return f(s)
+        return f(s + np.asarray(ds)) - f(s)
+
+    def _summary(self, name, **kw):
+        return process(t=self.t, x=getattr(self.x, name)(axis=-1, keepdims=True, **kw))
+
+    def psum(self):
+        return self._summary('sum')
+
+    def pmean(self):
+        return self._summary('mean')
+
+    def pvar(self, ddof=0):
+        return self._summary('var', ddof=ddof)
+
+    def pstd(self, ddof=0):
+        return self._summary('std', ddof=ddof)
+
+    def pmin(self):
+        return self._summary('min')
+
+    def pmax(self):
+        return self._summary('max')
+
+
+class device_process:
+    """A process resident in HBM: ``x`` is a CUDA float64 tensor shaped
+    ``(N,) + vshape + (paths,)`` (paths contiguous, the reference's layout,
+    integration.py:550), ``t`` the host timeline.  ``pmean/pvar/pstd`` run the
+    reduction kernels and return small host ``process`` objects shaped
+    ``(N,) + vshape + (1,)`` as the reference does (infrastructure.py:
+    861-889)."""
+
+    def __init__(self, t, x):
+        self.t = np.asarray(t).reshape(-1)
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float64):
+            raise TypeError('device_process needs a CUDA float64 tensor')
+        if x.shape[0] != self.t.size:
+            raise ValueError('process could not be created from timeline t '
+                             'shaped {} and body shaped {}'
+                             .format(self.t.shape, tuple(x.shape)))
+        self.x = x
+
+    shape = property(lambda self: tuple(self.x.shape))
+    paths = property(lambda self: self.x.shape[-1])
+    vshape = property(lambda self: tuple(self.x.shape[1:-1]))
+    ndim = property(lambda self: self.x.dim())
+    dtype = property(lambda self: np.dtype(float))
+
+    def __len__(self):
+        return self.x.shape[0]
+
+    def __getitem__(self, key):
+        """Integer / slice on the time axis keep the container; anything else
+        returns the indexed tensor."""
+        if isinstance(key, slice):
+            return device_process(self.t[key], self.x[key])
+        return self.x[key]
+
+    def cpu(self):
+        return process(t=self.t, x=self.x.cpu().numpy())
+
+    to_process = cpu
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.x.cpu().numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def _rows(self):
+        x = self.x if self.x.is_contiguous() else self.x.contiguous()
+        return x.reshape(-1, x.shape[-1])
+
+    def _moments(self, centre=None):
+        return _cuda.moments(self._rows(), self.paths, centre)
+
+    def _wrap(self, flat):
+        return process(t=self.t, x=np.asarray(flat).reshape(self.shape[:-1] + (1,)))
+
+    def psum(self):
+        return self._wrap(self._moments()[:, 0])
+
+    def pmean(self):
+        m = self._moments()
+        c = m[:, 0]/self.paths
+        # second pass centred on the first-pass mean: two-pass accuracy
+        m2 = self._moments(centre=c)
+        return self._wrap(c + m2[:, 0]/self.paths)
+
+    def pvar(self, ddof=0):
+        n = self.paths
+        c = self._moments()[:, 0]/n
+        m = self._moments(centre=c)
+        d = m[:, 0]/n
+        return self._wrap((m[:, 1] - n*d*d)/(n - ddof))
+
+    def pstd(self, ddof=0):
+        return self._wrap(np.sqrt(np.asarray(self.pvar(ddof=ddof)).reshape(-1)))
+
+    def pmin(self):
+        return self._wrap(self._moments()[:, 4])
+
+    def pmax(self):
+        return self._wrap(self._moments()[:, 5])
+
+
+# --------------------------------------------------------------------------
+# sources
+# --------------------------------------------------------------------------
+
+class source:
+    """Base class of stochasticity sources (reference infrastructure.py:
+    1291-1382).  Any callable ``dz(t, dt)`` with ``paths`` and ``vshape``
+    attributes obeys the source protocol."""
+
+    def __init__(self, *, paths=1, vshape=(), dtype=None, rng=None, seed=None):
+        self.paths, self.dtype = paths, dtype
+        self.vshape = _shape_setup(vshape)
+        if isinstance(rng, (int, np.int64, list, np.ndarray)):
+            raise TypeError('`rng` must be an instance of a random number '
+                            'generator, not {}.'.format(type(rng)))
+        self._rng = default_rng if rng is None else rng
+        # Philox key: explicit seed, or 64 bits drawn from the generator
+        self.seed = int(seed) if seed is not None else _seed_from(self._rng)
+        self._epoch = 0      # bumped per integration / standalone call
+
+    def __call__(self, t, dt=None):
+        dt = 0 if dt is None else dt
+        return np.asarray(t) + np.asarray(dt) + np.nan
+
+    @property
+    def rng(self):
+        return self._rng
+
+    @property
+    def size(self):
+        return 0
+
+    @property
+    def t(self):
+        return np.array((), dtype=float)
+
+    def next_key(self):
+        """Fresh 64-bit Philox key for one integration (or one draw call):
+        successive runs of the same instance are independent, the same
+        (seed, call index) always reproduces the same stream."""
+        key = _splitmix64(self.seed + self._epoch)
+        self._epoch += 1
+        return key
+
+
+def _chol(corr):
+    corr = np.asarray(corr, dtype=float)
+    if corr.ndim == 3:
+        if corr.shape[2] != 1:
+            raise ValueError('invalid correlation matrix shape {}'
+                             .format(corr.shape))
+        corr = corr[..., 0]
+    try:
+        return np.linalg.cholesky(corr)
+    except np.linalg.LinAlgError:
+        # semi-definite matrices (e.g. |rho| = 1): symmetric square root made
+        # triangular by QR keeps L L^T = corr
+        w, v = np.linalg.eigh(corr)
+        if w.min() < -1e-10:
+            raise ValueError('correlation matrix is not positive semidefinite')
+        a = v*np.sqrt(np.clip(w, 0, None))
+        q, r = np.linalg.qr(a.T)
+        L = r.T
+        return L*np.sign(np.diag(L) + (np.diag(L) == 0))
+
+
+class wiener_source(source):
+    """dw: standard Wiener increments, optionally correlated along the last
+    axis of ``vshape`` (reference infrastructure.py:1388-1560).  Inside an
+    integration the draws are generated in-kernel (Philox4x32-10 -> Box-Muller
+    -> Cholesky factor of ``corr`` evaluated at ``t + dt/2``); as a standalone
+    callable ``dw(t, dt)`` launches ``sdeb_draw_wiener`` and returns a host
+    array ``vshape + (paths,)``."""
+
+    def __init__(self, *, paths=1, vshape=(), dtype=None, rng=None,
+                 corr=None, rho=None, seed=None):
+        super().__init__(paths=paths, vshape=vshape, dtype=dtype, rng=rng, seed=seed)
+        self.corr = corr = _corr_matrix(corr, rho)
+        cshape = _param_shape(corr)
+        if corr is not None:
+            if self.vshape == ():
+                raise ValueError('if vshape is (), no correlations apply, but '
+                                 'corr={}, rho={} were given'.format(corr, rho))
+            if cshape is not None and (
+                    cshape[:2] != 2*self.vshape[-1:] or
+                    (len(cshape) == 3 and cshape[-1] != 1)):
+                raise ValueError(
+                    'cannot instantiate a Wiener source with values shape {} '
+                    'and correlation matrix shape {}'.format(self.vshape, cshape))
+
+    def chol_at(self, t):
+        """Lower Cholesky factor of the correlation in force at time ``t``
+        (None if uncorrelated)."""
+        if self.corr is None:
+            return None
+        c = self.corr(t) if callable(self.corr) else self.corr
+        return _chol(c)
+
+    def __call__(self, t, dt):
+        t, dt = np.broadcast_arrays(t, dt)
+        if t.shape != ():
+            out = np.empty(t.shape + self.vshape + (self.paths,))
+            for i in np.ndindex(t.shape):
+                out[i] = self(t[i], dt[i])
+            return out
+        dev = _cuda.device()
+        vs = self.vshape
+        correlated = self.corr is not None
+        ndw = vs[-1] if correlated else 1
+        groups = int(np.prod(vs[:-1] if correlated else vs, dtype=int))
+        if ndw > 32:
+            raise NotImplementedError('more than 32 correlated components')
+        L = self.chol_at(float(t) + float(dt)/2)
+        chol = None
+        if L is not None:
+            chol = _cuda.to_device(L[np.tril_indices(ndw)], dev)
+        out = _cuda.empty((groups*ndw, self.paths), dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.sdeb_draw_wiener(
+                _cuda.ptr(out), groups, ndw, self.paths, self.paths, 0,
+                self.next_key(), 0, float(np.sqrt(np.abs(dt))),
+                _cuda.ptr(chol), _cuda.stream_ptr(dev)))
+        return out.cpu().numpy().reshape(vs + (self.paths,))
+
+
+class poisson_source(source):
+    """dn: Poisson increments with intensity ``lam`` (reference
+    infrastructure.py:1566-1633): ``sign(dt)*Poisson(|dt|*lam(t+dt/2))``."""
+
+    def __init__(self, *, paths=1, vshape=(), dtype=int, rng=None, lam=1.,
+                 seed=None):
+        super().__init__(paths=paths, vshape=vshape, dtype=dtype, rng=rng, seed=seed)
+        self.lam = lam = _variable_param_setup(lam)
+        ls = _param_shape(lam)
+        if ls is not None:
+            try:
+                np.broadcast_to(np.empty(ls), self.vshape + (paths,))
+            except ValueError:
+                raise ValueError(
+                    'cannot broadcast lambda parameter shaped {} to requested '
+                    'poisson source shape = vshape + (paths,) = {}'
+                    .format(ls, self.vshape + (paths,)))
+
+    def lam_at(self, t):
+        return np.asarray(self.lam(t) if callable(self.lam) else self.lam,
+                          dtype=float)
+
+    def __call__(self, t, dt):
+        dj, dn = _draw_cpoisson(self, self, None, t, dt, want_dj=False)
+        return dn
+
+
+class _law:
+    """Jump-size law with possibly time-dependent parameters (reference
+    infrastructure.py:1640-1776).  ``at(t)`` gives (kind, a, b, pa)."""
+
+    def __init__(self, kind, **params):
+        self.kind, self.params = kind, params
+
+    def at(self, t):
+        v = {k: (np.asarray(z(t)) if callable(z) else np.asarray(z))
+             for k, z in self.params.items()}
+        a = np.asarray(v.get('a', 0.), dtype=float)
+        b = np.asarray(v.get('b', 0.), dtype=float)
+        pa = np.asarray(v.get('pa', 0.), dtype=float)
+        if self.kind == _lib.LAW_EXP and (a == 0).any():
+            raise ValueError('domain error in arguments')
+        if self.kind == _lib.LAW_DOUBLE_EXP and (
+                (a <= 0).any() or (b <= 0).any() or (pa > 1).any() or (pa < 0).any()):
+            raise ValueError('domain error in arguments')
+        return self.kind, a, b, pa
+
+    # moments used by analytical formulae (reference 1719, 1727, 1743-1791)
+    def _const(self):
+        return self.at(0.)[1:]
+
+    def mean(self):
+        a, b, pa = self._const()
+        return {_lib.LAW_NORMAL: a, _lib.LAW_UNIFORM: (a + b)/2,
+                _lib.LAW_EXP: a, _lib.LAW_DOUBLE_EXP: pa*a - (1 - pa)*b}[self.kind] + 0
+
+    def var(self):
+        a, b, pa = self._const()
+        return {_lib.LAW_NORMAL: b*b, _lib.LAW_UNIFORM: (b - a)**2/12,
+                _lib.LAW_EXP: a*a,
+                _lib.LAW_DOUBLE_EXP: pa*(1 - pa)*(a + b)**2 + (pa*a**2 + (1 - pa)*b**2)
+                }[self.kind] + 0
+
+    def std(self):
+        return np.sqrt(self.var())
+
+    def exp_mean(self):
+        a, b, pa = self._const()
+        if self.kind == _lib.LAW_NORMAL:
+            return np.exp(a + b*b/2) + 0
+        if self.kind == _lib.LAW_UNIFORM:
+            return (np.exp(b) - np.exp(a))/(b - a) + 0
+        if self.kind == _lib.LAW_EXP:
+            return np.where(a < 1, 1/(1 - a), np.inf) + 0
+        return (pa/(1 - a) if a < 1 else np.inf) + (1 - pa)/(1 + b) + 0
+
+
+def norm_rv(a=0, b=1):
+    """Normal jump sizes, mean ``a`` and standard deviation ``b``
+    (reference infrastructure.py:1653-1664)."""
+    return _law(_lib.LAW_NORMAL, a=a, b=b)
+
+
+def uniform_rv(a=0, b=1):
+    """Uniform jump sizes in [a, b] (reference 1667-1677)."""
+    return _law(_lib.LAW_UNIFORM, a=a, b=b)
+
+
+def exp_rv(a=1):
+    """Exponential jump sizes with (signed) scale ``a`` (reference 1680-1693)."""
+    return _law(_lib.LAW_EXP, a=a)
+
+
+def double_exp_rv(a=1, b=1, pa=0.5):
+    """Double exponential: scale ``a`` with probability ``pa``, ``-b``
+    otherwise (reference 1696-1712)."""
+    return _law(_lib.LAW_DOUBLE_EXP, a=a, b=b, pa=pa)
+
+
+class cpoisson_source(source):
+    """dj: compound Poisson increments (reference infrastructure.py:
+    1881-2040).  With a preset law (``norm_rv`` ...) the draws happen
+    in-kernel; after a standalone call ``dn_value`` holds the counts."""
+
+    def __init__(self, *, paths=1, vshape=(), dtype=None, rng=None, dn=None,
+                 ptype=int, lam=1., y=None, seed=None):
+        super().__init__(paths=paths, vshape=vshape, dtype=dtype, rng=rng, seed=seed)
+        self.dn = _source_setup(dn, poisson_source, paths=paths,
+                                vshape=self.vshape, dtype=ptype, rng=rng, lam=lam)
+        self.ptype = self.dn.dtype if hasattr(dn, 'dtype') else ptype
+        self.lam = self.dn.lam if hasattr(dn, 'lam') else lam
+        self.y = uniform_rv(a=0, b=1) if y is None else y
+
+    def device_ready(self):
+        """True when both the counts and the sizes can be drawn in-kernel."""
+        return type(self.dn) is poisson_source and isinstance(self.y, _law)
+
+    def __call__(self, t, dt):
+        if not self.device_ready():
+            raise NotImplementedError(
+                'cpoisson_source with a custom dn source or a non-preset jump '
+                'law has no device implementation')
+        dj, dn = _draw_cpoisson(self, self.dn, self.y, t, dt, want_dj=True)
+        self.dn_value = dn
+        return dj
+
+
+def lane_values(z, lead_shape, what='parameter'):
+    """Broadcast a (vshape-wise) parameter value to one scalar per lane.
+    Parameters follow the reference's convention of broadcasting against
+    ``vshape + (paths,)``; values that really vary along the paths axis are not
+    supported on the device path."""
+    z = np.asarray(z, dtype=float)
+    try:
+        return np.broadcast_to(z, tuple(lead_shape) + (1,)).reshape(-1).copy()
+    except ValueError:
+        raise NotImplementedError(
+            '{} of shape {} does not broadcast to vshape + (1,) = {}: '
+            'path-dependent parameters are not supported by the CUDA path'
+            .format(what, z.shape, tuple(lead_shape) + (1,)))
+
+
+def _draw_cpoisson(src, dn_src, law, t, dt, want_dj):
+    t, dt = np.broadcast_arrays(t, dt)
+    if t.shape != ():
+        raise NotImplementedError('array-valued t, dt')
+    t, dt = float(t), float(dt)
+    dev = _cuda.device()
+    vs, paths = src.vshape, src.paths
+    lanes = int(np.prod(vs, dtype=int))
+    lam = lane_values(dn_src.lam_at(t + dt/2), vs, 'lam')
+    if law is not None:
+        kind, a, b, pa = law.at(t + dt/2)
+    else:
+        kind, a, b, pa = _lib.LAW_UNIFORM, 0., 1., 0.
+    a, b, pa = (lane_values(z, vs, 'jump law parameter') for z in (a, b, pa))
+    dj = _cuda.empty((lanes, paths), dev) if want_dj else None
+    dn = _cuda.empty((lanes, paths), dev, torch.int64)
+    key = src.next_key()
+    sign = int(np.sign(dt))
+    with torch.cuda.device(dev):
+        for i in range(lanes):   # one launch per lane: parameters may differ
+            _lib.check(_lib.lib.sdeb_draw_cpoisson(
+                _cuda.ptr(dj[i]) if want_dj else None, _cuda.ptr(dn[i]), 1,
+                paths, paths, 0, (key + i) & 0xFFFFFFFFFFFFFFFF, 0,
+                float(abs(dt)*lam[i]), sign, kind, float(a[i]), float(b[i]),
+                float(pa[i]), _cuda.stream_ptr(dev)))
+    dn_h = dn.cpu().numpy().reshape(vs + (paths,)).astype(dn_src.dtype, copy=False)
+    dj_h = dj.cpu().numpy().reshape(vs + (paths,)) if want_dj else None
+    return dj_h, dn_h
+
+
+class replay_source:
+    """Replay-mode source: a table of pre-drawn increments, one entry per
+    integration step, e.g. the increments logged from the reference's own
+    sources.  ``table[n]`` must be shaped ``vshape + (paths,)`` (host ndarray
+    or CUDA tensor); ``dn`` optionally carries the Poisson counts of a compound
+    source (exposed as ``dn_value`` like the reference's cpoisson_source,
+    infrastructure.py:2038)."""
+
+    def __init__(self, table, dn=None):
+        self.table = table
+        self.dn_table = dn
+        shape = tuple(table.shape)
+        self.paths, self.vshape = shape[-1], shape[1:-1]
+        self.steps = shape[0]
+        self._i = 0
+
+    def __call__(self, t, dt):
+        z = self.table[self._i]
+        if self.dn_table is not None:
+            self.dn_value = self.dn_table[self._i]
+        self._i += 1
+        return z
+
+
+# --------------------------------------------------------------------------
+# montecarlo
+# --------------------------------------------------------------------------
+
+class montecarlo:
+    """Cumulated summary statistics of Monte Carlo samples (reference
+    infrastructure.py:2718-3312): mean, centred moments 1..4 (centre = mean of
+    the first sample, 2934), and one histogram per component whose bins are
+    fixed by the first sample (2999-3004).  Samples may be host arrays, CUDA
+    tensors or ``device_process`` rows; the reductions always run on the GPU
+    (``sdeb_moments`` / ``sdeb_histogram``)."""
+
+    def __init__(self, sample=None, axis=-1, bins=100, range=None, use='all',
+                 dtype=None, ctype=np.int64, device=None):
+        self.dtype, self.ctype = dtype, ctype
+        self._paths = [0]
+        self._bins, self._range, self._use = bins, range, use
+        self._device = device
+        self._mean = self._moments = self._counts = None
+        if sample is not None:
+            self.update(sample, axis=axis)
+
+    paths = property(lambda self: self._paths[0])
+
+    @property
+    def vshape(self):
+        if self._moments is None:
+            raise ValueError('no sample data: vshape not defined')
+        return self._moments[0].shape
+
+    @property
+    def shape(self):
+        return self.vshape + (self.paths,)
+
+    def _as_device(self, sample, axis):
+        if isinstance(sample, device_process):
+            sample = sample.x
+        if isinstance(sample, torch.Tensor):
+            if not sample.is_cuda:
+                sample = sample.to(_cuda.device(self._device))
+            x = sample.to(torch.float64)
+        else:
+            a = np.asarray(sample)
+            if a.ndim == 0:
+                a = a.reshape(1)
+            x = _cuda.to_device(np.moveaxis(a, axis, -1), _cuda.device(self._device),
+                                dtype=float)
+            axis = -1
+        if x.dim() == 0:
+            x = x.reshape(1)
+        x = x.movedim(axis, -1).contiguous()
+        return x
+
+    def update(self, sample, axis=-1):
+        """Add a sample (reference infrastructure.py:2869-2922)."""
+        if self._use not in ('all', 'even', 'odd'):
+            raise ValueError("use must be one of 'all', 'even', 'odd', not {}"
+                             .format(self._use))
+        if self._use != 'all':
+            raise NotImplementedError(
+                "antithetic use='even'/'odd' is outside the accelerated path")
+        x = self._as_device(sample, axis)
+        vshape, m = tuple(x.shape[:-1]), x.shape[-1]
+        rows = x.reshape(-1, m)
+        first = self.paths == 0
+        n = self.paths
+        if first:
+            dtype = float if self.dtype is None else self.dtype
+            self._moments = tuple(np.zeros(vshape, dtype=dtype) for _ in range(4))
+            self._mean = np.zeros(vshape, dtype=dtype)
+            pass1 = _cuda.moments(rows, m)
+            self._center = (pass1[:, 0]/m).reshape(vshape).astype(dtype)
+            lo, hi = pass1[:, 4], pass1[:, 5]
+        st = _cuda.moments(rows, m, centre=self._center.reshape(-1))
+        for k in range(4):
+            mk = (st[:, k]/m).reshape(vshape)
+            self._moments[k][...] = (n*self._moments[k] + m*mk)/(n + m)
+        smean = self._center + (st[:, 0]/m).reshape(vshape)
+        self._mean[...] = (n*self._mean + m*smean)/(n + m)
+        if self._bins is not None:
+            if first:
+                self._setup_bins(vshape, lo, hi)
+            self._update_histogram(rows, m)
+        self._paths[0] += m
+
+    def _setup_bins(self, vshape, lo, hi):
+        bins = self._bins
+        nrow = int(np.prod(vshape, dtype=int))
+        self._edges, self._uniform = [], []
+        if isinstance(bins, str):
+            raise NotImplementedError(
+                'data-driven bin estimators ({!r}) are not available on the '
+                'device: pass an integer or explicit edges'.format(bins))
+        if isinstance(bins, (int, np.integer)):
+            for i in range(nrow):
+                if self._range is not None:
+                    a, b = map(float, self._range)
+                    if a > b:
+                        raise ValueError('max must be larger than min in range parameter.')
+                else:
+                    a, b = float(lo[i]), float(hi[i])
+                if not (np.isfinite(a) and np.isfinite(b)):
+                    raise ValueError('autodetected range of [{}, {}] is not finite'.format(a, b))
+                if a == b:                       # numpy's histogram convention
+                    a, b = a - 0.5, b + 0.5
+                self._edges.append(np.linspace(a, b, int(bins) + 1))
+                self._uniform.append(True)
+        else:
+            arr = np.asarray(bins)
+            if arr.dtype == object and arr.shape == vshape:
+                rows = [np.asarray(arr[i], dtype=float) for i in np.ndindex(vshape)]
+            elif arr.shape[:-1] == vshape:
+                rows = [np.asarray(arr[i], dtype=float) for i in np.ndindex(vshape)]
+            else:
+                raise ValueError(
+                    'shape of the bins {} not compatible with the shape {} of '
+                    'sample data points'.format(arr.shape, vshape))
+            for e in rows:
+                if (np.diff(e) < 0).any():
+                    raise ValueError('`bins` must increase monotonically, when an array')
+                self._edges.append(e)
+                self._uniform.append(False)
+        dev = _cuda.device(self._device)
+        self._counts_dev = [_cuda.zeros((len(e) - 1,), dev, torch.int64) for e in self._edges]
+        self._outside_dev = [_cuda.zeros((1,), dev, torch.int64) for _ in self._edges]
+        self._bins = np.empty(vshape, dtype=object)
+        for j, i in enumerate(np.ndindex(vshape)):
+            self._bins[i] = self._edges[j]
+
+    def _update_histogram(self, rows, m):
+        for j, e in enumerate(self._edges):
+            _cuda.histogram(rows[j], e, self._counts_dev[j], self._outside_dev[j],
+                            self._uniform[j])
+        vshape = self.vshape
+        self._counts = np.empty(vshape, dtype=object)
+        self._paths_outside = np.zeros(vshape, dtype=self.ctype)
+        for j, i in enumerate(np.ndindex(vshape)):
+            self._counts[i] = self._counts_dev[j].cpu().numpy().astype(self.ctype, copy=False)
+            self._paths_outside[i] = int(self._outside_dev[j].item())
+            if self._counts[i].sum() + self._paths_outside[i] != self.paths + m:
+                raise RuntimeError(
+                    'total number of cumulated paths inconsistent with stored '
+                    'cumulated counts')
+
+    def __getitem__(self, i):
+        a = montecarlo(bins=self._bins if self.paths == 0 else None)
+        a._paths = self._paths
+        a.dtype, a.ctype = self.dtype, self.ctype
+        if self.paths != 0:
+            a._mean = self._mean[i]
+            a._moments = tuple(mm[i] for mm in self._moments)
+            if self._counts is not None:
+                a._bins = self._bins[i]
+                a._counts = self._counts[i]
+                a._paths_outside = self._paths_outside[i]
+        return a
+
+    # statistics (reference infrastructure.py:3043-3076)
+    def mean(self):
+        return self._mean
+
+    def var(self):
+        m1, m2 = self._moments[:2]
+        return 0.*m1 if self.paths < 2 else m2 - m1*m1
+
+    def std(self):
+        return np.sqrt(self.var())
+
+    def skew(self):
+        m1, m2, m3 = self._moments[:3]
+        return (0.*m1 if self.paths < 2 else
+                (m3 - 3*m1*m2 + 2*m1**3)/(m2 - m1*m1)**1.5)
+
+    def kurtosis(self):
+        # as in the reference (3062-3067) the value for paths >= 2 is the raw,
+        # not the excess, kurtosis
+        m1, m2, m3, m4 = self._moments[:4]
+        return (-3.0 + 0.*m1 if self.paths < 2 else
+                (m4 - 4*m1*m3 + 6*m1*m1*m2 - 3*m1**4)/(m2 - m1*m1)**2)
+
+    def stderr(self):
+        return np.nan if self.paths < 2 else np.sqrt(self.var()/(self.paths - 1))
+
+    def __repr__(self):
+        if self.paths == 0:
+            return '<empty montecarlo object>'
+        mean, err = np.asarray(self.mean()), np.asarray(self.stderr())
+        if mean.size == 1 and err.size == 1:
+            mean, err = mean.flatten()[0], err.flatten()[0]
+        return repr(mean) + ' +/- ' + repr(err)
+
+    def histogram(self):
+        """(counts, bins) of the cumulated samples (reference 3090-3115)."""
+        if self.paths == 0 or self._bins is None or self._counts is None:
+            raise ValueError('no distribution data available')
+        counts, bins = self._counts, self._bins
+        if isinstance(counts, np.ndarray) and counts.dtype == object:
+            if counts.size > 1:
+                raise IndexError(
+                    'histograms and distributions must be invoked on '
+                    'single-valued montecarlo instances; use indexing to '
+                    'select the value to be addressed (es. ``a[i].histogram()``)')
+            counts, bins = counts.flatten()[0], bins.flatten()[0]
+        return counts, bins
+
+    def density_histogram(self):
+        counts, bins = self.histogram()
+        return counts/counts.sum()/np.diff(bins), bins
+
+    @property
+    def outpaths(self):
+        self.histogram()
+        return self._paths_outside
+
+    def outerr(self):
+        return self.outpaths/self.paths
+
+    m = property(lambda self: self.mean())
+    s = property(lambda self: self.std())
+    e = property(lambda self: self.stderr())
+    h = property(lambda self: self.histogram())
+    dh = property(lambda self: self.density_histogram())
+
+    @property
+    def stats(self):
+        return dict(mean=self.mean(), stderr=self.stderr(), std=self.std(),
+                    skew=self.skew(), kurtosis=self.kurtosis())

@@ -1,0 +1,198 @@
+"""GPU tests of the in-kernel Philox draws: generator accuracy, distribution,
+cross-mode consistency (philox == replay of its own dumped increments) and
+moments against closed forms / the oracle within 3-4 standard errors."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sde_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def sd():
+    import sdepy_b200
+    return sdepy_b200
+
+
+def test_normal_pair_matches_libdevice():
+    from sdepy_b200 import _lib, _cuda
+    n = 1 << 20
+    zf = torch.empty(2*n, dtype=torch.float64, device='cuda')
+    zl = torch.empty(2*n, dtype=torch.float64, device='cuda')
+    _lib.check(_lib.lib.sdeb_test_normals(1234, n, _cuda.ptr(zf), _cuda.ptr(zl),
+                                          _cuda.stream_ptr(zf.device)))
+    zf, zl = zf.cpu().numpy(), zl.cpu().numpy()
+    assert np.isfinite(zf).all()
+    # hand-rolled log / sqrt / sincos vs libdevice on identical bits
+    assert np.abs(zf - zl).max() < 2e-14
+    z = zf[128:]
+    assert abs(z.mean()) < 4/np.sqrt(z.size)
+    assert abs(z.var() - 1) < 4*np.sqrt(2/z.size)
+    assert abs((z**4).mean() - 3) < 4*np.sqrt(96/z.size)
+    import scipy.stats
+    assert scipy.stats.kstest(z[:200000], 'norm').pvalue > 1e-4
+    # pairs are uncorrelated
+    assert abs(np.mean(z[0::2]*z[1::2])) < 4/np.sqrt(z.size/2)
+
+
+def test_philox_mode_equals_replay_of_its_own_increments():
+    """Same step arithmetic in both noise modes: dump the Philox increments,
+    feed them to the CPU oracle and to the kernel in replay mode."""
+    m = sd()
+    paths, n = 5000, 40
+    grid = np.linspace(0., 1., n + 1)
+    par = dict(mu=.03, sigma=1., theta=.04, k=2., xi=.9)
+    P = m.full_heston_process(paths=paths, steps=grid, x0=100., y0=.04, rho=-.7,
+                              seed=11, **par)
+    P._dump_increments = True
+    x, y = P((0., .5, 1.))
+    dW = P._last_run.dump[0]['dW'].cpu().numpy()
+    (ox, oy), oinfo = orc.euler_replay('heston', par, 100., grid, [0, 20, 40],
+                                       dW, y0=.04, full=True)
+    assert np.array_equal(np.asarray(y), oy)
+    assert np.abs(np.asarray(x)/ox - 1).max() <= 4*np.finfo(float).eps
+    assert np.array_equal(P.info['negative_y_count'], oinfo['negative_y_count'])
+    # distribution of the dumped increments
+    z = dW/np.sqrt(np.diff(grid))[:, None, None]
+    assert abs(z.mean()) < 4/np.sqrt(z.size)
+    c = np.corrcoef(z[:, 0].ravel(), z[:, 1].ravel())[0, 1]
+    assert abs(c + .7) < 4/np.sqrt(z.size/2)
+    # reproducible: same seed, same stream; different call, new stream
+    Q = m.full_heston_process(paths=paths, steps=grid, x0=100., y0=.04, rho=-.7,
+                              seed=11, **par)
+    x2, y2 = Q((0., .5, 1.))
+    assert np.array_equal(np.asarray(y2), np.asarray(y))
+    x3, y3 = Q((0., .5, 1.))
+    assert not np.array_equal(np.asarray(y3), np.asarray(y))
+
+
+def test_sharding_is_invisible():
+    """Counter = global path index: two shards reproduce the single run."""
+    m = sd()
+    kw = dict(steps=30, x0=1., mu=.05, sigma=.2, seed=5)
+    full = np.asarray(m.lognorm_process(paths=1000, **kw)((0., 1.)))
+    a = np.asarray(m.lognorm_process(paths=600, path_offset=0, **kw)((0., 1.)))
+    b = np.asarray(m.lognorm_process(paths=400, path_offset=600, **kw)((0., 1.)))
+    assert np.array_equal(full, np.concatenate((a, b), axis=-1))
+
+
+def test_config1_lognorm_terminal_moments():
+    """BASELINE config 1: lognorm 1e5 paths x 250 steps, pmean/pstd vs the
+    closed forms of sdepy.analytical.lognorm_mean/std (analytical.py:133,165)."""
+    m = sd()
+    paths = 100_000
+    x = m.lognorm_process(x0=1., mu=.05, sigma=.2, paths=paths, seed=1234,
+                          output='device')(np.linspace(0, 1, 251))
+    mean, std = float(np.asarray(x.pmean())[-1, 0]), float(np.asarray(x.pstd())[-1, 0])
+    em = np.exp(.05)
+    es = em*np.sqrt(np.exp(.2**2) - 1)
+    assert abs(mean - em) < 3.5*es/np.sqrt(paths)
+    assert abs(std - es) < 3.5*es*np.sqrt(1.5/paths)   # lognormal kurtosis margin
+    xs = np.asarray(x)
+    assert np.allclose(np.asarray(x.pmean())[..., 0], xs.mean(axis=-1), rtol=1e-13)
+    assert np.allclose(np.asarray(x.pvar())[..., 0], xs.var(axis=-1), rtol=1e-11)
+
+
+def test_ou_hw_discrete_euler_moments():
+    """Linear SDEs: compare with the exact moments of the DISCRETE Euler
+    recursion m <- m + k(theta-m)dt, v <- (1-k dt)^2 v + sigma^2 dt."""
+    m = sd()
+    paths, n = 400_000, 100
+    k, theta, sigma, T = 1., .2, .3, 2.
+    x = m.ornstein_uhlenbeck_process(paths=paths, steps=n + 1, x0=.1, theta=theta,
+                                     k=k, sigma=sigma, seed=3, output='device')((0., T))
+    dt = T/n
+    mm, vv = .1, 0.
+    for _ in range(n):
+        mm, vv = mm + k*(theta - mm)*dt, (1 - k*dt)**2*vv + sigma**2*dt
+    mean = float(np.asarray(x.pmean())[-1, 0]); var = float(np.asarray(x.pvar())[-1, 0])
+    assert abs(mean - mm) < 4*np.sqrt(vv/paths)
+    assert abs(var - vv) < 4*vv*np.sqrt(2/paths)
+
+
+def test_heston_stats_vs_oracle_sample():
+    """Philox Heston vs the oracle's own numpy-driven sample (the reference's
+    draws): log-mean and log-variance within combined standard errors; fused
+    'stats' output equals the statistics of the stored paths."""
+    m = sd()
+    paths = 400_000
+    par = dict(mu=.03, sigma=1., theta=.04, k=2., xi=.3)
+    grid = np.linspace(0., 1., 65)
+    kw = dict(paths=paths, steps=grid, x0=100., y0=.04, rho=-.7, seed=99, **par)
+    xd = m.heston_process(output='device', **kw)((0., 1.))
+    xT = xd.x[-1].cpu().numpy()
+    oT, _ = orc.heston_stream(par, 100., .04, -.7, grid, 200_000,
+                              np.random.default_rng(1))
+    la, lb = np.log(xT), np.log(oT)
+    se = np.sqrt(la.var()/la.size + lb.var()/lb.size)
+    assert abs(la.mean() - lb.mean()) < 4*se
+    assert abs(la.var() - lb.var()) < 5*la.var()*np.sqrt(2/la.size + 2/lb.size)*1.5
+    # fused statistics (same seed => same paths)
+    st = m.heston_process(output='stats', payoff=('call', 100., np.exp(-.03)), **kw)((0., 1.))
+    assert np.allclose(np.asarray(st.pmean())[-1, 0], xT.mean(), rtol=1e-12)
+    assert np.allclose(np.asarray(st.pvar())[-1, 0], xT.var(), rtol=1e-10)
+    pay = np.maximum(xT - 100., 0.)*np.exp(-.03)
+    assert np.allclose(np.asarray(st.payoff_mean())[-1, 0], pay.mean(), rtol=1e-12)
+    assert np.asarray(st.pmin())[-1, 0] == xT.min()
+    assert np.asarray(st.pmax())[-1, 0] == xT.max()
+    # Gil-Pelaez price from sdepy.analytical.heston_log_chf:
+    # 9.2425; Euler/full-truncation bias is below the 4-se band at this size
+    price, err = np.asarray(st.payoff_mean())[-1, 0], np.asarray(st.payoff_stderr())[-1, 0]
+    assert abs(price - 9.2425) < 4*err + 0.03
+
+
+def test_merton_kou_moments_and_jump_counts():
+    m = sd()
+    paths = 200_000
+    lam, a, b = 2., -.1, .15
+    P = m.merton_jumpdiff_process(paths=paths, steps=101, x0=1., mu=.05, sigma=.2,
+                                  lam=lam, a=a, b=b, seed=4)
+    P._dump_increments = True
+    x = np.asarray(P((0., 1.)))
+    lx = np.log(x[-1])
+    mean = (.05 - .02) + lam*a
+    var = .04 + lam*(a*a + b*b)
+    assert abs(lx.mean() - mean) < 4*np.sqrt(var/paths)
+    assert abs(lx.var() - var) < 6*var*np.sqrt(2/paths)
+    jc = P.info['jump_count']
+    assert abs(jc.mean() - lam) < 4*np.sqrt(lam/paths)
+    assert abs(jc.var() - lam) < 6*lam*np.sqrt(2/paths)
+    d = P._last_run.dump[0]
+    dN = d['dN'].cpu().numpy()
+    assert np.array_equal(dN.sum(axis=0).reshape(jc.shape), jc)
+    assert np.allclose(P.info['jump_rate'][0], dN.sum()/paths, rtol=1e-12)
+    # replaying the dumped increments reproduces the run bit for bit
+    R = m.merton_jumpdiff_process(
+        paths=paths, steps=101, x0=1., mu=.05, sigma=.2,
+        dw=m.replay_source(d['dW'].reshape(100, paths)),
+        dj=m.replay_source(d['dJ'].reshape(100, paths), dn=d['dN'].reshape(100, paths)))
+    xr = np.asarray(R((0., 1.)))
+    assert np.array_equal(xr, x)
+    assert np.array_equal(R.info['jump_count'], jc)
+    # Kou: mean of the double exponential = pa*a - (1-pa)*b
+    K = m.kou_jumpdiff_process(paths=paths, steps=101, x0=1., mu=.05, sigma=.2,
+                               lam=lam, a=.1, b=.15, pa=.4, seed=6)
+    lk = np.log(np.asarray(K((0., 1.)))[-1])
+    ym = .4*.1 - .6*.15
+    yv = .4*.6*(.25)**2 + (.4*.01 + .6*.0225)
+    assert abs(lk.mean() - (.03 + lam*ym)) < 4*np.sqrt((.04 + lam*(yv + ym*ym))/paths)
+
+
+def test_time_dependent_correlation_hw3():
+    m = sd()
+    from tests.cases import HW
+    paths = 100_000
+    P = m.hull_white_process(paths=paths, steps=51, seed=8, **HW)
+    P._dump_increments = True
+    x = P(np.linspace(0, 5, 11))
+    assert x.shape == (11, paths) and np.isfinite(np.asarray(x)).all()
+    dW = P._last_run.dump[0]['dW'].cpu().numpy()      # [50, 3, paths]
+    grid = np.linspace(0, 5, 51)
+    for n in (0, 25, 49):
+        z = dW[n]/np.sqrt(grid[n + 1] - grid[n])
+        c = np.corrcoef(z)
+        want = HW['corr'](grid[n] + (grid[n + 1] - grid[n])/2)
+        assert np.abs(c - want).max() < 5/np.sqrt(paths)

@@ -1,0 +1,78 @@
+"""GPU tests of the reductions: device_process.pmean/pvar/pstd and montecarlo
+(moments within 1e-12 relative of the reference's values, histogram counts
+and out-of-range counts bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sde_oracle as orc
+from tests.cases import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def sd():
+    import sdepy_b200
+    return sdepy_b200
+
+
+def test_psummaries_match_reference():
+    m = sd()
+    g = golden('stats_lognorm')
+    dp = m.device_process(g['t'], torch.from_numpy(g['x']).cuda())
+    assert np.allclose(np.asarray(dp.pmean()), g['pmean'], rtol=1e-14, atol=0)
+    assert np.allclose(np.asarray(dp.pvar()), g['pvar'], rtol=1e-12, atol=0)
+    assert np.allclose(np.asarray(dp.pstd()), g['pstd'], rtol=1e-12, atol=0)
+    assert np.allclose(np.asarray(dp.pvar(ddof=1)), g['pvar1'], rtol=1e-12, atol=0)
+    assert dp.pmean().shape == g['pmean'].shape
+    assert np.array_equal(np.asarray(dp.pmin())[..., 0], g['x'].min(axis=-1))
+    assert np.array_equal(np.asarray(dp.pmax())[..., 0], g['x'].max(axis=-1))
+    assert np.array_equal(np.asarray(dp.cpu()), g['x'])
+
+
+@pytest.mark.parametrize('where', ['host', 'device'])
+def test_montecarlo_one_shot_and_chunked(where):
+    m = sd()
+    g = golden('stats_lognorm')
+    xT = g['x'][-1]
+
+    def put(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).cuda() if where == 'device' else a
+    one = m.montecarlo(put(xT), bins=25)
+    chunk = m.montecarlo(bins=25)
+    for c in (xT[:, :1500], xT[:, 1500:2700], xT[:, 2700:]):
+        chunk.update(put(c))
+    for tag, a in (('one', one), ('chunk', chunk)):
+        assert a.paths == xT.shape[-1]
+        assert np.allclose(a.mean(), g[tag + '_mean'], rtol=1e-13, atol=0)
+        assert np.allclose(a.var(), g[tag + '_var'], rtol=1e-11, atol=0)
+        assert np.allclose(a.std(), g[tag + '_std'], rtol=1e-11, atol=0)
+        assert np.allclose(a.stderr(), g[tag + '_stderr'], rtol=1e-11, atol=0)
+        assert np.allclose(a.skew(), g[tag + '_skew'], rtol=1e-9, atol=0)
+        assert np.allclose(a.kurtosis(), g[tag + '_kurt'], rtol=1e-9, atol=0)
+        for i in range(2):
+            counts, edges = a[i].histogram()
+            assert np.array_equal(edges, g[tag + '_edges'][i])
+            assert np.array_equal(counts, g[tag + '_counts'][i])
+            assert a[i].outpaths == g[tag + '_outpaths'][i]
+
+
+def test_histogram_semantics_large_random():
+    """Half-open bins, last bin closed, values on edges, explicit edges."""
+    m = sd()
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=3_000_017)
+    x[:1000] = np.linspace(-3, 3, 1000)          # many values exactly on edges
+    a = m.montecarlo(x, bins=60, range=(-3., 3.))
+    c, e = np.histogram(x, bins=60, range=(-3., 3.))
+    counts, edges = a.histogram()
+    assert np.array_equal(edges, e) and np.array_equal(counts, c)
+    assert a.outpaths == x.size - c.sum()
+    edges2 = np.array([-2., -1.5, -.2, 0., .1, 1.7, 4.])
+    b = m.montecarlo(x, bins=edges2)
+    c2, _ = np.histogram(x, bins=edges2)
+    assert np.array_equal(b.histogram()[0], c2)
+    o = orc.moments_histogram(bins=60, range=(-3., 3.))
+    o.update(x)
+    assert np.allclose(a.mean(), o.mean(), rtol=1e-10, atol=1e-15)
+    assert np.allclose(a.var(), o.var(), rtol=1e-12)

@@ -1,0 +1,170 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol of
+include/sdeb.h, the ctypes structs match the header, host-side lowering
+(step grid, sweeps, parameter records, error conventions) is right, and
+compute entry points fail loudly without a device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import sdepy_b200 as sd
+from sdepy_b200 import _engine, _lib
+from oracle import sde_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+no_gpu = not torch.cuda.is_available()
+
+
+def test_library_exports_header_symbols():
+    header = open(os.path.join(ROOT, 'include', 'sdeb.h')).read()
+    declared = set(re.findall(r'\b(sdeb_[a-z0-9_]+)\s*\(', header))
+    declared -= {'sdeb_plan_t'}
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(_lib.lib, name), name
+    assert _lib.lib.sdeb_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layout_matches_header():
+    header = open(os.path.join(ROOT, 'include', 'sdeb.h')).read()
+    body = header[header.index('typedef struct sdeb_problem {'):header.index('} sdeb_problem;')]
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    names = re.findall(r'(\w+);', body)
+    assert names == [f[0] for f in _lib.Problem._fields_]
+    assert ctypes.sizeof(_lib.Problem) == 8*len(names)
+    body = header[header.index('typedef struct sdeb_plan_t {'):header.index('} sdeb_plan_t;')]
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    assert re.findall(r'(\w+);', body) == [f[0] for f in _lib.Plan._fields_]
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10."""
+    assert _lib.philox((0, 0, 0, 0), (0, 0)) == (
+        0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert _lib.philox((0xffffffff,)*4, (0xffffffff,)*2) == (
+        0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert _lib.philox((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344),
+                       (0xa4093822, 0x299f31d0)) == (
+        0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+
+
+def test_plan_shapes():
+    for model, n, want in [
+            (_lib.MODEL_LINEAR, 1, (1, 1, 1, 2, 2)),
+            (_lib.MODEL_LINEAR_LOG, 3, (3, 3, 3, 6, 12)),
+            (_lib.MODEL_JUMPDIFF, 1, (1, 1, 1, 8, 8)),
+            (_lib.MODEL_HULL_WHITE, 3, (3, 3, 1, 9, 15)),
+            (_lib.MODEL_HESTON, 1, (2, 2, 1, 6, 9)),
+            (_lib.MODEL_HESTON_FULL, 2, (4, 4, 4, 12, 22))]:
+        s = _engine.problem_spec(model, n, 1)
+        assert (s.nw, s.ndw, s.nx, s.npc, s.npt) == want
+    with pytest.raises(_lib.SdebError):
+        _engine.problem_spec(_lib.MODEL_HESTON, 7, 1)
+
+
+def test_step_grid_and_sweeps_follow_reference():
+    P = sd.ornstein_uhlenbeck_process(paths=3, steps=(0.1, .2, .21, .5, .93, 1.5))
+    tt = np.array((0., .37, 1.))
+    target = P.pace(tt)
+    target = target[(target >= 0.) & (target <= 1.)]
+    grid = np.unique(np.concatenate((target, tt)))
+    assert np.array_equal(grid, orc.step_grid(tt, (0.1, .2, .21, .5, .93, 1.5))[1])
+    seg, = _engine.segments_of(tt, grid, 0)
+    assert seg.row0 == 0 and list(seg.store_row) == [-1, -1, -1, 1, -1, -1, 2]
+    assert np.array_equal(seg.ds, np.diff(grid))
+    back, fwd = _engine.segments_of(tt, grid, 1)
+    assert np.array_equal(back.s, grid[4:0:-1]) and (back.ds < 0).all()
+    assert list(back.store_row) == [-1, -1, -1, 0] and back.row0 == 1
+    assert list(fwd.store_row) == [-1, -1, 2]
+    last, = _engine.segments_of(tt, grid, -1)
+    assert (last.ds < 0).all() and last.row0 == 2
+
+
+def test_heston_records_and_initial_state():
+    P = sd.heston_process(paths=10, steps=20, x0=100., y0=.04, mu=.03, sigma=.5,
+                          theta=.04, k=2., xi=.3, rho=-.7, seed=3)
+    assert (P.vshape, P.xshape, P.wshape) == ((), (), (2,))
+    spec, lead = P._spec()
+    seg, = _engine.segments_of(np.array([0., 1.]), np.linspace(0, 1, 5), 0)
+    rec = P._records(spec, seg, lead, False)
+    assert rec.shape == (1, 1, 9)
+    L = np.linalg.cholesky(np.array([[1, -.7], [-.7, 1]]))
+    assert np.allclose(rec[0, 0], [.03, .5*.5/2, .5, .04, 2., .3, 1., L[1, 0], L[1, 1]])
+    w0 = P._initial_state(0.)
+    assert np.array_equal(w0[:, 0], [np.log(100.), .04])
+    # time-dependent parameter => one record per step, evaluated at the left point
+    Q = sd.ornstein_uhlenbeck_process(paths=4, theta=lambda t: .2 + .1*t)
+    spec, lead = Q._spec()
+    rec = Q._records(spec, seg, lead, False)
+    assert rec.shape == (4, 1, 3) and np.allclose(rec[:, 0, 0], .2 + .1*seg.s)
+
+
+def test_vshape_lanes():
+    P = sd.lognorm_process(paths=5, vshape=(2, 3), x0=1.)
+    assert P._lanes() == ((2, 3), 1)
+    C = sd.lognorm_process(paths=5, vshape=(2, 3), corr=np.eye(3))
+    assert C._lanes() == ((2,), 3)
+    H = sd.hull_white_process(paths=5, vshape=(4,), factors=2)
+    assert H._lanes() == ((4,), 2) and H.wshape == (4, 2) and H.xshape == (4,)
+    F = sd.full_heston_process(paths=5, vshape=(2,))
+    assert F.wshape == (4,) and F._lanes() == ((), 2)
+    with pytest.raises(NotImplementedError):
+        B = sd.lognorm_process(paths=5, mu=np.arange(5.))
+        spec, lead = B._spec()
+        seg, = _engine.segments_of(np.array([0., 1.]), np.array([0., 1.]), 0)
+        B._records(spec, seg, lead, False)
+
+
+def test_construction_errors():
+    with pytest.raises(TypeError):
+        sd.lognorm_process(paths=10, nonexistent=1.)
+    with pytest.raises(ValueError):
+        sd.lognorm_process(paths=10, method='nonexistent')
+    with pytest.raises(ValueError):
+        sd.wiener_source(paths=3, vshape=(), rho=.5)
+    with pytest.raises(ValueError):
+        sd.wiener_source(paths=3, vshape=(3,), rho=.5)
+    with pytest.raises(TypeError):
+        sd.wiener_source(paths=3, rng=1234)
+    with pytest.raises(TypeError):
+        class bad(sd.SDE):
+            pass
+        bad()
+    s = sd.wiener_source(paths=3, vshape=(4,), rho=(.1, .2))
+    assert s.corr.shape == (4, 4) and s.corr[0, 2] == .1 and s.corr[1, 3] == .2
+
+
+def test_same_seed_same_keys():
+    a = sd.wiener_source(paths=3, rng=np.random.default_rng(7))
+    b = sd.wiener_source(paths=3, rng=np.random.default_rng(7))
+    assert a.seed == b.seed and a.next_key() == b.next_key()
+    assert a.next_key() != a.next_key()
+    c = sd.wiener_source(paths=3, seed=42)
+    assert c.seed == 42
+
+
+def test_process_container():
+    t = np.linspace(0, 1, 5)
+    x = np.arange(5*2*3, dtype=float).reshape(5, 2, 3)
+    p = sd.process(t, x=x)
+    assert p.paths == 3 and p.vshape == (2,)
+    assert np.array_equal(np.asarray(p.pmean()), x.mean(axis=-1, keepdims=True))
+    assert np.array_equal(np.asarray(p.pvar(ddof=1)), x.var(axis=-1, ddof=1, keepdims=True))
+    assert np.allclose(p(.125), (x[0] + x[1])/2)
+    assert np.allclose(p(.25, .25), x[2] - x[1])
+    with pytest.raises(ValueError):
+        sd.process(t, x=x[:4])
+
+
+@pytest.mark.skipif(not no_gpu, reason='only meaningful without a device')
+def test_no_cpu_fallback():
+    with pytest.raises(RuntimeError):
+        sd.lognorm_process(paths=10, steps=5)((0., 1.))
+    with pytest.raises(RuntimeError):
+        sd.montecarlo(np.arange(10.))
+    out = ctypes.c_double()
+    rc = _lib.lib.sdeb_fp64_peak(10, ctypes.byref(out), None)
+    assert rc != 0 and _lib.lib.sdeb_last_error()
