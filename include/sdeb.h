@@ -91,6 +91,10 @@ typedef struct sdeb_problem {
     const int32_t* store_row; /* [n_steps]: row storing the state after step n
                                  (integration.py:386 exact-equality store), -1 = none */
     const double* params;     /* [n_psteps][n_groups][npt] records, see sdeb_plan */
+    const double* params_host;/* optional HOST copy of the same records: a single
+                                 time-invariant record (n_psteps == n_groups == 1)
+                                 is then passed in the kernel-argument constant
+                                 bank (no registers, no loads in the step loop) */
     const double* w0;         /* initial WORKING state (after init/log,
                                  integration.py:1161-1164): [n_groups][nw] (+[pitch]) */
     const double* dW;         /* replay: [n_steps][n_groups*ndw][pitch]         */

@@ -13,8 +13,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(CSRC, 'libsdeb.so')
-SOURCES = ['sdeb.cu']
-DEPS = ['sdeb.cu', 'sde_engine.cuh', os.path.join('..', '..', 'include', 'sdeb.h')]
+SOURCES = ['sdeb.cu', 'sdeb_models_heston.cu', 'sdeb_models_linear.cu',
+           'sdeb_models_meanrev.cu']
+DEPS = SOURCES + ['sde_engine.cuh', 'sdeb_internal.h',
+                  os.path.join('..', '..', 'include', 'sdeb.h')]
+NVCC_FLAGS = ['-Xcompiler', '-fPIC', '-O3', '-std=c++17',
+              '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo']
 
 
 def nvcc_path():
@@ -34,17 +38,32 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [nvcc_path(), '-shared', '-Xcompiler', '-fPIC', '-O3', '-std=c++17',
-           '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
-           '-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ['-ldl']
-    if verbose:
-        cmd.insert(1, '-Xptxas=-v')
-        print(' '.join(cmd))
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    nvcc = nvcc_path()
+    extra = os.environ.get('SDEB_NVCC_FLAGS', '').split()
+    objdir = os.path.join(CSRC, 'build')
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for src in SOURCES:     # one nvcc per translation unit, in parallel
+        obj = os.path.join(objdir, src.replace('.cu', '.o'))
+        cmd = [nvcc, '-c'] + NVCC_FLAGS + extra + (['-Xptxas=-v'] if verbose else []) + [
+            '-o', obj, os.path.join(CSRC, src)]
+        if verbose:
+            print(' '.join(cmd))
+        procs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE,
+                                                 stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for cmd, obj, proc in procs:
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError('nvcc failed: %s\n%s' % (' '.join(cmd), out))
+        if verbose:
+            print(out)
+        objs.append(obj)
+    link = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a',
+            '-o', LIB] + objs + ['-ldl']
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError('link failed:\n' + res.stdout + res.stderr)
     return LIB
 
 

@@ -133,6 +133,8 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
         keep += [steps_d, rows_d, rec_d]
         p.steps, p.store_row = steps_d.data_ptr(), rows_d.data_ptr()
         p.params, p.w0 = rec_d.data_ptr(), w0_d.data_ptr()
+        p.params_host = rec.ctypes.data          # rec stays alive in `keep`
+        keep.append(rec)
         if replay is not None:
             tabs = replay[k]
             for name in ('dW', 'dJ', 'dN'):
@@ -254,6 +256,8 @@ class resident_stats_run:
         b = self._bufs
         p.steps, p.store_row = b['steps'].data_ptr(), b['rows'].data_ptr()
         p.params, p.w0 = b['rec'].data_ptr(), b['w0'].data_ptr()
+        self._rec_host = rec
+        p.params_host = rec.ctypes.data
         p.centre, p.stats = b['centre'].data_ptr(), b['stats'].data_ptr()
         if sde.payoff is not None:
             kind, strike, scale = sde.payoff

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'csrc', 'libsdeb.so')
+LIB_PATH = os.environ.get('SDEB_LIB') or os.path.join(HERE, 'csrc', 'libsdeb.so')
 
 ABI_VERSION = 1
 NSTAT = 8
@@ -30,7 +30,8 @@ class Problem(C.Structure):
         ('n_groups', i64), ('n_rows', i64), ('row0', i64),
         ('n_psteps', i64), ('w0_per_path', i64), ('reserved0', i64),
         ('seed', u64),
-        ('steps', ptr), ('store_row', ptr), ('params', ptr), ('w0', ptr),
+        ('steps', ptr), ('store_row', ptr), ('params', ptr),
+        ('params_host', ptr), ('w0', ptr),
         ('dW', ptr), ('dJ', ptr), ('dN', ptr), ('out', ptr), ('stats', ptr),
         ('centre', ptr),
         ('payoff_kind', i64), ('payoff_strike', f64), ('payoff_scale', f64),

@@ -12,8 +12,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/sdeb.h"
-#include "sde_engine.cuh"
+#include "sdeb_internal.h"
 
 using namespace sdeb;
 
@@ -53,22 +52,8 @@ extern "C" int sdeb_device_info(int64_t* sm_count, int64_t* cc_major, int64_t* c
 }
 
 // ---------------------------------------------------------------------------
-// model registry (pre-instantiated presets)
+// model registry: pre-instantiated presets live in sdeb_models_*.cu
 // ---------------------------------------------------------------------------
-struct ModelInfo {
-    const void* fn;
-    int nw, ndw, nx, npc, ncnt, jumps;
-};
-
-template <class M>
-static ModelInfo info_of() {
-    ModelInfo mi;
-    mi.fn = (const void*)&integrate_kernel<M>;
-    mi.nw = M::NW; mi.ndw = M::NDW; mi.nx = M::NX; mi.npc = M::NPC;
-    mi.ncnt = M::NCNT; mi.jumps = M::JUMPS;
-    return mi;
-}
-
 struct JitModule {
     cudaLibrary_t lib;
     cudaKernel_t kernel;
@@ -79,63 +64,21 @@ static std::map<int64_t, JitModule> g_jit;
 static int64_t g_jit_next = 1;
 
 static bool lookup_model(int64_t model, int64_t n, int64_t jit_handle, ModelInfo& mi) {
-    switch (model) {
-    case SDEB_MODEL_LINEAR:
-        if (n == 1) { mi = info_of<LinearSDE<1, false, false>>(); return true; }
-        if (n == 2) { mi = info_of<LinearSDE<2, false, false>>(); return true; }
-        if (n == 3) { mi = info_of<LinearSDE<3, false, false>>(); return true; }
-        if (n == 4) { mi = info_of<LinearSDE<4, false, false>>(); return true; }
-        return false;
-    case SDEB_MODEL_LINEAR_LOG:
-        if (n == 1) { mi = info_of<LinearSDE<1, true, false>>(); return true; }
-        if (n == 2) { mi = info_of<LinearSDE<2, true, false>>(); return true; }
-        if (n == 3) { mi = info_of<LinearSDE<3, true, false>>(); return true; }
-        if (n == 4) { mi = info_of<LinearSDE<4, true, false>>(); return true; }
-        return false;
-    case SDEB_MODEL_JUMPDIFF:
-        if (n == 1) { mi = info_of<LinearSDE<1, true, true>>(); return true; }
-        if (n == 2) { mi = info_of<LinearSDE<2, true, true>>(); return true; }
-        return false;
-    case SDEB_MODEL_MEANREV:
-        if (n == 1) { mi = info_of<MeanRevertingSDE<1, false>>(); return true; }
-        if (n == 2) { mi = info_of<MeanRevertingSDE<2, false>>(); return true; }
-        if (n == 3) { mi = info_of<MeanRevertingSDE<3, false>>(); return true; }
-        if (n == 4) { mi = info_of<MeanRevertingSDE<4, false>>(); return true; }
-        return false;
-    case SDEB_MODEL_HULL_WHITE:
-        if (n == 1) { mi = info_of<MeanRevertingSDE<1, true>>(); return true; }
-        if (n == 2) { mi = info_of<MeanRevertingSDE<2, true>>(); return true; }
-        if (n == 3) { mi = info_of<MeanRevertingSDE<3, true>>(); return true; }
-        if (n == 4) { mi = info_of<MeanRevertingSDE<4, true>>(); return true; }
-        return false;
-    case SDEB_MODEL_CIR:
-        if (n == 1) { mi = info_of<CoxIngersollRossSDE<1>>(); return true; }
-        if (n == 2) { mi = info_of<CoxIngersollRossSDE<2>>(); return true; }
-        return false;
-    case SDEB_MODEL_HESTON:
-        if (n == 1) { mi = info_of<HestonSDE<1, false>>(); return true; }
-        if (n == 2) { mi = info_of<HestonSDE<2, false>>(); return true; }
-        return false;
-    case SDEB_MODEL_HESTON_FULL:
-        if (n == 1) { mi = info_of<HestonSDE<1, true>>(); return true; }
-        if (n == 2) { mi = info_of<HestonSDE<2, true>>(); return true; }
-        return false;
-    case SDEB_MODEL_JIT: {
+    if (model == SDEB_MODEL_JIT) {
         std::lock_guard<std::mutex> lock(g_jit_mutex);
         auto it = g_jit.find(jit_handle);
         if (it == g_jit.end()) return false;
         mi = it->second.mi;
         return true;
     }
-    default:
-        return false;
-    }
+    return sdeb_lookup_heston(model, n, mi) || sdeb_lookup_linear(model, n, mi) ||
+           sdeb_lookup_meanrev(model, n, mi);
 }
 
 // ---------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------
-static const int kThreads = 256;
+static const int kThreads = SDEB_THREADS;
 static const int64_t kMaxStatsSmem = 96 * 1024;   // accumulators kept in smem up to here
 
 static int64_t smem_bytes(const ModelInfo& mi, const sdeb_problem* p, bool stats_in_kernel) {
@@ -143,7 +86,14 @@ static int64_t smem_bytes(const ModelInfo& mi, const sdeb_problem* p, bool stats
     int64_t npt = mi.npc + nch;
     int64_t d = TAB_DOUBLES + 2 * STEP_CHUNK + (int64_t)STEP_CHUNK * npt + 8 * NSTAT * mi.nx;
     if (stats_in_kernel) d += p->n_rows * p->n_groups * mi.nx * NSTAT;
-    return d * 8 + STEP_CHUNK * 4;
+    return d * 8 + STEP_CHUNK * 4 + 16;
+}
+
+// the lean kernel serves the hot configuration: Philox draws, one
+// time-invariant parameter record (passed through the constant bank), no dump
+static bool use_lean(const sdeb_problem* p, const ModelInfo& mi) {
+    return mi.fn_lean && p->noise == SDEB_NOISE_PHILOX && p->params_host &&
+           p->n_psteps == 1 && p->n_groups == 1 && !p->dW_dump && !p->dJ_dump && !p->dN_dump;
 }
 
 static int plan_impl(const sdeb_problem* p, sdeb_plan_t* plan, ModelInfo& mi, bool need_device) {
@@ -174,14 +124,15 @@ static int plan_impl(const sdeb_problem* p, sdeb_plan_t* plan, ModelInfo& mi, bo
     int64_t tiles = ((p->n_paths + kThreads - 1) / kThreads) * p->n_groups;
     int sm = 148, occ = 2;
     int dev = 0;
+    const void* fn = use_lean(p, mi) ? mi.fn_lean : mi.fn;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) {
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
         if (plan->smem_bytes > 48 * 1024)
-            cudaFuncSetAttribute(mi.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)plan->smem_bytes);
         int o = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, mi.fn, kThreads,
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, kThreads,
                                                           (size_t)plan->smem_bytes) == cudaSuccess && o > 0)
             occ = o;
     } else {
@@ -239,6 +190,14 @@ extern "C" int sdeb_integrate(const sdeb_problem* p, void* stream_) {
     }
     KArgs a;
     memset(&a, 0, sizeof a);
+    { static const NrmK nk = {SDEB_NRMK_VALUES}; a.nk = nk; }
+    philox_round_keys(p->seed, a.rkey);
+    const bool lean = use_lean(p, mi);
+    if (lean) {
+        // single time-invariant record: serve it from the constant bank
+        for (int k = 0; k < plan.npt; ++k) a.pc[k] = p->params_host[k];
+        a.use_pc = 1;
+    }
     a.n_paths = p->n_paths; a.path_offset = p->path_offset; a.pitch = p->pitch;
     a.n_steps = (int)p->n_steps; a.n_groups = (int)p->n_groups; a.n_rows = (int)p->n_rows;
     a.row0 = (int)p->row0; a.n_psteps = (int)p->n_psteps; a.w0_per_path = (int)p->w0_per_path;
@@ -253,7 +212,7 @@ extern "C" int sdeb_integrate(const sdeb_problem* p, void* stream_) {
     a.dW_dump = p->dW_dump; a.dJ_dump = p->dJ_dump; a.dN_dump = (i64*)p->dN_dump;
 
     void* args[] = {&a};
-    CUDA_TRY(cudaLaunchKernel(mi.fn, dim3((unsigned)plan.blocks), dim3(kThreads), args,
+    CUDA_TRY(cudaLaunchKernel(lean ? mi.fn_lean : mi.fn, dim3((unsigned)plan.blocks), dim3(kThreads), args,
                               (size_t)plan.smem_bytes, stream));
     if (p->stats) {
         int64_t len = p->n_rows * p->n_groups * mi.nx * NSTAT;
@@ -402,7 +361,7 @@ extern "C" int sdeb_histogram(const double* x, int64_t n, const double* edges, i
 // standalone source draws
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-draw_wiener_kernel(double* out, int n_groups, int ndw, int64_t n_paths, int64_t pitch,
+draw_wiener_kernel(const NrmK nk, double* out, int n_groups, int ndw, int64_t n_paths, int64_t pitch,
                    int64_t path_offset, u64 seed, u32 step, double sq, const double* chol) {
     __shared__ double tab[TAB_DOUBLES];
     fill_tables(tab);
@@ -411,14 +370,16 @@ draw_wiener_kernel(double* out, int n_groups, int ndw, int64_t n_paths, int64_t 
     const int g = blockIdx.y;
     if (path >= n_paths) return;
     const u64 gpath = (u64)(path_offset + path);
+    u32 rk[20];
+    philox_round_keys(seed, rk);
     Rng rng;
-    rng.k0 = (u32)seed; rng.k1 = (u32)(seed >> 32);
+    rng.rk = rk;
     rng.c_x = (u32)gpath; rng.c_y = ((u32)(gpath >> 32) & 0xFFu) | ((u32)g << 8);
     rng.step = step;
     double z[34];
     for (int b = 0; b < (ndw + 1) / 2; ++b) {
         U4 w = rng.block((u32)b);
-        normal_pair(w, tab, 1.0, z[2*b], z[2*b + 1]);
+        normal_pair(w, tab, nk, 1.0, z[2*b], z[2*b + 1]);
     }
     for (int r = ndw - 1; r >= 0; --r) {
         double acc = z[r];
@@ -439,14 +400,15 @@ extern "C" int sdeb_draw_wiener(double* out, int64_t n_groups, int64_t ndw, int6
         return fail(SDEB_EINVAL, "sdeb_draw_wiener: bad arguments (ndw <= 32, n_groups <= 65535)");
     cudaStream_t stream = (cudaStream_t)stream_;
     dim3 grid((unsigned)((n_paths + 255) / 256), (unsigned)n_groups);
-    draw_wiener_kernel<<<grid, 256, 0, stream>>>(out, (int)n_groups, (int)ndw, n_paths, pitch,
+    static const NrmK nk = {SDEB_NRMK_VALUES};
+    draw_wiener_kernel<<<grid, 256, 0, stream>>>(nk, out, (int)n_groups, (int)ndw, n_paths, pitch,
                                                  path_offset, seed, (u32)step, sqrt_abs_dt, chol);
     CUDA_TRY(cudaGetLastError());
     return SDEB_OK;
 }
 
 __global__ void __launch_bounds__(256)
-draw_cpoisson_kernel(double* dj, i64* dn, int64_t n_paths, int64_t pitch, int64_t path_offset,
+draw_cpoisson_kernel(const NrmK nk, double* dj, i64* dn, int64_t n_paths, int64_t pitch, int64_t path_offset,
                      u64 seed, u32 step, double lamdt, double explam, int sign, int law,
                      double a, double b, double pa) {
     __shared__ double tab[TAB_DOUBLES];
@@ -456,8 +418,10 @@ draw_cpoisson_kernel(double* dj, i64* dn, int64_t n_paths, int64_t pitch, int64_
     const int g = blockIdx.y;
     if (path >= n_paths) return;
     const u64 gpath = (u64)(path_offset + path);
+    u32 rk[20];
+    philox_round_keys(seed, rk);
     Rng rng;
-    rng.k0 = (u32)seed; rng.k1 = (u32)(seed >> 32);
+    rng.rk = rk;
     rng.c_x = (u32)gpath; rng.c_y = ((u32)(gpath >> 32) & 0xFFu) | ((u32)g << 8);
     rng.step = step;
     U4 w = rng.block((u32)STREAM_POISSON);
@@ -465,7 +429,7 @@ draw_cpoisson_kernel(double* dj, i64* dn, int64_t n_paths, int64_t pitch, int64_
     double sum = 0.0;
     for (int j = 0; j < k; ++j) {
         U4 wj = rng.block((u32)(STREAM_JUMP + j));
-        double yj = jump_size(wj, tab, law, a, b, pa);
+        double yj = jump_size(wj, tab, nk, law, a, b, pa);
         sum = (j == 0) ? yj : sum + yj;
     }
     if (dj) dj[(int64_t)g * pitch + path] = sign * sum;
@@ -481,7 +445,8 @@ extern "C" int sdeb_draw_cpoisson(double* dj, int64_t* dn, int64_t n_lanes, int6
         return fail(SDEB_EINVAL, "sdeb_draw_cpoisson: bad arguments");
     cudaStream_t stream = (cudaStream_t)stream_;
     dim3 grid((unsigned)((n_paths + 255) / 256), (unsigned)n_lanes);
-    draw_cpoisson_kernel<<<grid, 256, 0, stream>>>(dj, (i64*)dn, n_paths, pitch, path_offset, seed,
+    static const NrmK nk = {SDEB_NRMK_VALUES};
+    draw_cpoisson_kernel<<<grid, 256, 0, stream>>>(nk, dj, (i64*)dn, n_paths, pitch, path_offset, seed,
                                                    (u32)step, lam_abs_dt, exp(-lam_abs_dt),
                                                    (int)sign, (int)law, a, b, pa);
     CUDA_TRY(cudaGetLastError());
@@ -491,14 +456,16 @@ extern "C" int sdeb_draw_cpoisson(double* dj, int64_t* dn, int64_t n_lanes, int6
 // ---------------------------------------------------------------------------
 // self tests / measurement
 // ---------------------------------------------------------------------------
-__global__ void test_normals_kernel(u64 seed, int64_t n, double* zf, double* zl) {
+__global__ void test_normals_kernel(const NrmK nk, u64 seed, int64_t n, double* zf, double* zl) {
     __shared__ double tab[TAB_DOUBLES];
     fill_tables(tab);
     __syncthreads();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    u32 rk[20];
+    philox_round_keys(seed, rk);
     Rng rng;
-    rng.k0 = (u32)seed; rng.k1 = (u32)(seed >> 32);
+    rng.rk = rk;
     rng.c_x = (u32)i; rng.c_y = (u32)(i >> 32); rng.step = 0;
     U4 w = rng.block(0);
     if (i < 64) {   // force the extreme corners of the bit space through both maps
@@ -509,15 +476,16 @@ __global__ void test_normals_kernel(u64 seed, int64_t n, double* zf, double* zl)
         if (i & 16) w.w = 0xFFFFFFFFu;
         if (i & 32) w.w = 0;
     }
-    normal_pair(w, tab, 1.0, zf[2*i], zf[2*i + 1]);
+    normal_pair(w, tab, nk, 1.0, zf[2*i], zf[2*i + 1]);
     normal_pair_libdevice(w, zl[2*i], zl[2*i + 1]);
 }
 
 extern "C" int sdeb_test_normals(uint64_t seed, int64_t n, double* z_fast, double* z_libdevice,
                                  void* stream_) {
     if (!z_fast || !z_libdevice || n < 1) return fail(SDEB_EINVAL, "sdeb_test_normals: bad arguments");
+    static const NrmK nk = {SDEB_NRMK_VALUES};
     test_normals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
-        seed, n, z_fast, z_libdevice);
+        nk, seed, n, z_fast, z_libdevice);
     CUDA_TRY(cudaGetLastError());
     return SDEB_OK;
 }
@@ -661,6 +629,7 @@ extern "C" int sdeb_jit_compile(const char* source, const char* model_type, int6
     if (dbytes < sizeof dims) return fail(SDEB_EJIT, "sdeb_jit_dims has the wrong size");
     CUDA_TRY(cudaMemcpy(dims, dptr, sizeof dims, cudaMemcpyDeviceToHost));
     jm.mi.fn = (const void*)jm.kernel;
+    jm.mi.fn_lean = NULL;
     jm.mi.nw = dims[0]; jm.mi.ndw = dims[1]; jm.mi.nx = dims[2]; jm.mi.npc = dims[3];
     jm.mi.ncnt = dims[4]; jm.mi.jumps = dims[5];
     std::lock_guard<std::mutex> lock(g_jit_mutex);

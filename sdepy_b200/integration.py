@@ -803,7 +803,10 @@ class _preset_SDE(SDE):
         n = max(n, 1) if seg.n_steps else 1
         ncomp = spec.ncomp
         rec = np.zeros((n, spec.groups, spec.npt))
-        full = tuple(lead) + (ncomp,)
+        # parameters broadcast against the working shape (+ a paths axis of 1);
+        # its prod(lead) x ncomp elements map to [group, component]
+        full = self._param_target()
+        assert int(np.prod(full, dtype=int)) == spec.groups*ncomp
         for i in range(n):
             s = seg.s[i] if seg.n_steps else 0.
             ds = seg.ds[i] if seg.n_steps else 0.
@@ -820,15 +823,18 @@ class _preset_SDE(SDE):
                 rec[i, :, spec.npc:] = _engine.chol_entries(L, spec.ndw)
         return rec
 
-    @staticmethod
-    def _lane_matrix(value, full):
+    def _param_target(self):
+        return self.wshape
+
+    def _lane_matrix(self, value, full):
         """Broadcast a coefficient against wshape (+ trailing paths axis of
         size 1) and reshape to [groups, ncomp]."""
         v = lane_values(value, full, 'SDE parameter')
-        return v.reshape(-1, full[-1])
+        return v.reshape(-1, self._lanes()[1])
 
     def _jump_cols(self, dj, s, ds, full, replay):
-        zero = np.zeros((int(np.prod(full[:-1], dtype=int)), full[-1]))
+        ncomp = self._lanes()[1]
+        zero = np.zeros((int(np.prod(full, dtype=int))//ncomp, ncomp))
         if replay:
             return [zero]*6
         mid = s + ds/2
@@ -971,6 +977,10 @@ class full_heston_SDE(_preset_SDE, SDEs):
     def _lanes(self):
         # one lane owns the N x- and N y-components of the last axis
         return self.wshape[:-1], self.wshape[-1]//2
+
+    def _param_target(self):
+        # parameters broadcast against vshape (x and y share them)
+        return self.wshape[:-1] + (self.wshape[-1]//2,)
 
     def _coeffs(self, p):
         sigma = p['sigma']

@@ -26,8 +26,12 @@ def test_normal_pair_matches_libdevice():
                                           _cuda.stream_ptr(zf.device)))
     zf, zl = zf.cpu().numpy(), zl.cpu().numpy()
     assert np.isfinite(zf).all()
-    # hand-rolled log / sqrt / sincos vs libdevice on identical bits
-    assert np.abs(zf - zl).max() < 2e-14
+    # hand-rolled log / sqrt / sincos vs libdevice on identical bits.  Both
+    # maps carry ~2e-16 ABSOLUTE error in s2 = -2 ln u, i.e. ~1e-16/r in
+    # z = r (cos, sin) -- only visible in the forced corner u -> 1 (r -> 0)
+    r = np.maximum(np.hypot(zl[0::2], zl[1::2]), 1e-300).repeat(2)
+    assert (np.abs(zf - zl) < 4e-15 + 3e-16/r).all()
+    assert np.abs(zf - zl)[128:].max() < 1e-13
     z = zf[128:]
     assert abs(z.mean()) < 4/np.sqrt(z.size)
     assert abs(z.var() - 1) < 4*np.sqrt(2/z.size)
