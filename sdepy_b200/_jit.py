@@ -1,0 +1,574 @@
+"""
+Run-time compilation of user-defined SDEs (the ``integrate`` decorator and
+direct ``SDE`` / ``SDEs`` subclasses with a Python ``sde`` method, reference
+``integration.py:1216-1225, 1711-1730, 1843-1955``).
+
+The Python ``sde(t, x, ..., **params)`` function cannot run inside a kernel,
+so it is TRACED: it is called once with symbolic state variables; every NumPy
+operation that touches a symbolic value is recorded as a node of an expression
+DAG, while sub-expressions that involve parameters only are evaluated by NumPy
+itself, exactly as the reference would, and enter the DAG as numeric LEAVES.
+The DAG is emitted as a step functor for ``csrc/sde_engine.cuh`` whose
+arithmetic uses the never-contracted ``__dmul_rn/__dadd_rn/...`` intrinsics in
+the recorded order (so replay mode stays bit-exact with the reference), and the
+leaves become the per-lane parameter record (re-traced at every step when they
+depend on time).  The source is compiled by NVRTC for sm_100a through
+``sdeb_jit_compile``.
+
+``method='milstein'`` adds the (1/2) b b' (dw^2 - dt) correction with b'
+obtained by symbolic differentiation of the diffusion node w.r.t. the
+equation's own variable (diagonal-noise Milstein).
+"""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+
+from . import _engine, _lib
+from .infrastructure import lane_values, wiener_source, cpoisson_source
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# --------------------------------------------------------------------------
+# expression DAG
+# --------------------------------------------------------------------------
+
+UNARY = {'negative': 'neg', 'positive': 'pos', 'absolute': 'abs', 'fabs': 'abs',
+         'sqrt': 'sqrt', 'exp': 'exp', 'log': 'log', 'sin': 'sin', 'cos': 'cos',
+         'tanh': 'tanh', 'square': 'square', 'log1p': 'log1p', 'expm1': 'expm1'}
+BINARY = {'add': 'add', 'subtract': 'sub', 'multiply': 'mul',
+          'true_divide': 'div', 'divide': 'div', 'maximum': 'max',
+          'minimum': 'min', 'power': 'pow'}
+
+
+class node:
+    """One value of the traced computation: a state variable, a numeric leaf
+    or an operation on other nodes.  Behaves like a NumPy scalar in
+    arithmetic so that user code runs unmodified."""
+
+    __array_priority__ = 1000.
+
+    def __init__(self, tracer, op, args=(), value=None, index=None):
+        self.tracer, self.op, self.args = tracer, op, tuple(args)
+        self.value, self.index = value, index
+        self.id = len(tracer.nodes)
+        tracer.nodes.append(self)
+
+    # ---- NumPy protocol ---------------------------------------------------
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != '__call__' or kwargs.get('out') is not None:
+            return NotImplemented
+        name = ufunc.__name__
+        t = self.tracer
+        if name in UNARY and len(inputs) == 1:
+            return t.apply(UNARY[name], inputs[0])
+        if name in BINARY and len(inputs) == 2:
+            return t.apply(BINARY[name], inputs[0], inputs[1])
+        raise TypeError(
+            'numpy.{} is not supported inside a traced sde function'.format(name))
+
+    def _bin(op):
+        def f(self, other):
+            return self.tracer.apply(op, self, other)
+
+        def r(self, other):
+            return self.tracer.apply(op, other, self)
+        return f, r
+
+    __add__, __radd__ = _bin('add')
+    __sub__, __rsub__ = _bin('sub')
+    __mul__, __rmul__ = _bin('mul')
+    __truediv__, __rtruediv__ = _bin('div')
+    __pow__, __rpow__ = _bin('pow')
+    del _bin
+
+    def __neg__(self):
+        return self.tracer.apply('neg', self)
+
+    def __pos__(self):
+        return self
+
+    def __abs__(self):
+        return self.tracer.apply('abs', self)
+
+    def __bool__(self):
+        raise TypeError('the truth value of a traced state variable is not '
+                        'defined: data-dependent Python branches cannot be '
+                        'compiled (use numpy.maximum / minimum)')
+
+    def __getitem__(self, key):
+        raise TypeError('indexing the state inside a traced sde function is '
+                        'not supported: the function is applied per component')
+
+    shape = ()
+    ndim = 0
+    dtype = np.dtype(float)
+
+
+class tracer:
+    def __init__(self):
+        self.nodes, self.leaves = [], []
+
+    def var(self, index):
+        return node(self, 'var', index=index)
+
+    def leaf(self, value):
+        v = np.asarray(value, dtype=float)
+        n = node(self, 'leaf', value=v, index=len(self.leaves))
+        # python scalars are structural constants, arrays are parameters
+        n.literal = isinstance(value, (int, float)) and not isinstance(value, (bool, np.generic))
+        self.leaves.append(n)
+        return n
+
+    def lift(self, z):
+        return z if isinstance(z, node) else self.leaf(z)
+
+    def apply(self, op, *args):
+        if op == 'pos':
+            return self.lift(args[0])
+        if op == 'pow':
+            base, ex = args
+            if not isinstance(ex, node):
+                exv = np.asarray(ex, dtype=float)
+                if exv.shape == () and float(exv) == 2.0:
+                    # numpy evaluates x**2 as x*x (fast scalar power)
+                    return self.apply('square', base)
+                if exv.shape == () and float(exv) == 1.0:
+                    return self.lift(base)
+                if exv.shape == () and float(exv) == 0.5:
+                    return self.apply('sqrt', base)
+        return node(self, op, [self.lift(a) for a in args])
+
+    def signature(self, roots):
+        """Structural fingerprint (ops and wiring, not leaf values)."""
+        parts = []
+        for n in self.nodes:
+            parts.append('%s:%s:%s' % (n.op, ','.join(str(a.id) for a in n.args),
+                                       n.index if n.op in ('var', 'leaf') else ''))
+        parts.append('|' + ';'.join(','.join('%s=%d' % (k, v.id) for k, v in r)
+                                    for r in roots))
+        return '\n'.join(parts)
+
+
+# symbolic derivative d(node)/d(var index)
+def diff(t, n, k, memo):
+    key = (n.id, k)
+    if key in memo:
+        return memo[key]
+    op, a = n.op, n.args
+    zero, one = 0.0, 1.0
+
+    def mul(u, v):
+        if isinstance(u, float) and u == 0.0 or isinstance(v, float) and v == 0.0:
+            return 0.0
+        if isinstance(u, float) and u == 1.0:
+            return v
+        if isinstance(v, float) and v == 1.0:
+            return u
+        return t.apply('mul', u, v)
+
+    def add(u, v):
+        if isinstance(u, float) and u == 0.0:
+            return v
+        if isinstance(v, float) and v == 0.0:
+            return u
+        return t.apply('add', u, v)
+
+    if op == 'var':
+        r = one if n.index == k else zero
+    elif op == 'leaf':
+        r = zero
+    else:
+        d = [diff(t, x, k, memo) for x in a]
+        if op == 'add':
+            r = add(d[0], d[1])
+        elif op == 'sub':
+            r = add(d[0], mul(-1.0, d[1]))
+        elif op == 'mul':
+            r = add(mul(d[0], a[1]), mul(a[0], d[1]))
+        elif op == 'div':
+            r = add(mul(d[0], t.apply('div', 1.0, a[1])),
+                    mul(mul(-1.0, d[1]), t.apply('div', n, a[1])))
+        elif op == 'neg':
+            r = mul(-1.0, d[0])
+        elif op == 'square':
+            r = mul(mul(2.0, a[0]), d[0])
+        elif op == 'sqrt':
+            r = mul(d[0], t.apply('div', 0.5, n))
+        elif op == 'exp':
+            r = mul(d[0], n)
+        elif op == 'log':
+            r = mul(d[0], t.apply('div', 1.0, a[0]))
+        elif op == 'sin':
+            r = mul(d[0], t.apply('cos', a[0]))
+        elif op == 'cos':
+            r = mul(d[0], t.apply('neg', t.apply('sin', a[0])))
+        elif op == 'tanh':
+            r = mul(d[0], t.apply('sub', 1.0, t.apply('square', n)))
+        elif op == 'pow':
+            if not (isinstance(d[1], float) and d[1] == 0.0):
+                raise NotImplementedError('derivative of x**y with variable y')
+            r = mul(d[0], t.apply('mul', a[1], t.apply('pow', a[0], t.apply('sub', a[1], 1.0))))
+        elif op in ('abs', 'max', 'min'):
+            if all(isinstance(x, float) and x == 0.0 for x in d):
+                r = zero
+            elif op == 'abs':
+                r = mul(d[0], t.apply('sign', a[0]))
+            else:
+                # d max(u, v) = [u >= v] du + [u < v] dv
+                sel = t.apply('ge' if op == 'max' else 'le', a[0], a[1])
+                r = add(mul(d[0], sel), mul(d[1], t.apply('sub', 1.0, sel)))
+        else:
+            raise NotImplementedError('derivative of ' + op)
+    memo[key] = r
+    return r
+
+
+# --------------------------------------------------------------------------
+# code generation
+# --------------------------------------------------------------------------
+
+C_OPS = {
+    'add': 'xadd({0}, {1})', 'sub': 'xsub({0}, {1})', 'mul': 'xmul({0}, {1})',
+    'div': '__ddiv_rn({0}, {1})', 'neg': '(-{0})', 'abs': 'fabs({0})',
+    'sqrt': 'xsqrt_any({0})', 'square': 'xmul({0}, {0})', 'exp': 'exp({0})',
+    'log': 'log({0})', 'sin': 'sin({0})', 'cos': 'cos({0})', 'tanh': 'tanh({0})',
+    'log1p': 'log1p({0})', 'expm1': 'expm1({0})', 'pow': 'pow({0}, {1})',
+    'max': 'xmax({0}, {1})', 'min': 'xmin({0}, {1})',
+    'sign': '(({0} > 0.0) - ({0} < 0.0))', 'ge': '(double)({0} >= {1})',
+    'le': '(double)({0} <= {1})',
+}
+
+PRELUDE = r'''
+namespace sdeb {
+// numpy semantics: np.maximum/minimum propagate the first operand when it is NaN
+__device__ __forceinline__ double xmax(double a, double b) { return (a >= b || a != a) ? a : b; }
+__device__ __forceinline__ double xmin(double a, double b) { return (a <= b || a != a) ? a : b; }
+__device__ __forceinline__ double xsqrt_any(double a) { return sqrt(a); }   // IEEE, like np.sqrt
+}
+'''
+
+
+def hexfloat(v):
+    v = float(v)
+    if v != v:
+        return '__longlong_as_double(0x7FF8000000000000LL)'
+    if v in (float('inf'), float('-inf')):
+        return ('-' if v < 0 else '') + '__longlong_as_double(0x7FF0000000000000LL)'
+    return float(v).hex() if v != int(v) or abs(v) > 1e15 else repr(float(v))
+
+
+class emitter:
+    """Emit C statements for the nodes reachable from a set of roots."""
+
+    def __init__(self, slot_of, var_expr):
+        self.slot_of, self.var_expr = slot_of, var_expr
+        self.lines, self.name = [], {}
+
+    def ref(self, n):
+        if n.id in self.name:
+            return self.name[n.id]
+        if n.op == 'var':
+            r = self.var_expr(n.index)
+        elif n.op == 'leaf':
+            r = hexfloat(n.value) if getattr(n, 'literal', False) else self.slot_of(n.index)
+        else:
+            args = [self.ref(a) for a in n.args]
+            r = 't%d' % n.id
+            self.lines.append('double %s = %s;' % (r, C_OPS[n.op].format(*args)))
+        self.name[n.id] = r
+        return r
+
+
+# --------------------------------------------------------------------------
+# traced SDE mixins
+# --------------------------------------------------------------------------
+
+_compiled = {}
+
+
+def _compile(source, name):
+    key = hashlib.sha1(source.encode()).hexdigest()
+    if key in _compiled:
+        return _compiled[key]
+    handle = C.c_int64()
+    log = C.create_string_buffer(1 << 16)
+    rc = _lib.lib.sdeb_jit_compile(source.encode(), name.encode(), C.byref(handle),
+                                   log, len(log))
+    if rc != 0:
+        raise _lib.SdebError('NVRTC compilation of the traced SDE failed: %s\n%s'
+                             % (_lib.lib.sdeb_last_error().decode('utf-8', 'replace'),
+                                log.value.decode('utf-8', 'replace')))
+    _compiled[key] = handle.value
+    return handle.value
+
+
+def engine_source():
+    with open(os.path.join(HERE, 'csrc', 'sde_engine.cuh')) as f:
+        return f.read()
+
+
+class _traced:
+    """Generic lowering of an SDE whose equation is a Python ``sde`` method:
+    base class of ``integration.SDE`` (the preset equations override it with
+    their hand-written kernel functors)."""
+
+    _device_schemes = ('euler', 'milstein')
+    _system = False          # True for SDEs (q equations)
+
+    @property
+    def _nvars(self):
+        return self.q if self._system else 1
+
+    @property
+    def _rec_comps(self):
+        return 1 if self._system else self._lanes()[1]
+
+    def _param_target(self):
+        return self.wshape[:-1] if self._system else self.wshape
+
+    def _trace(self, t):
+        """Call the user's sde at time t with symbolic variables.  Returns
+        (tracer, roots) with roots = one list of (id, node) per equation, in
+        the order the increments are summed (dict order for one equation,
+        integration.py:718; sorted ids for systems, where the reference
+        iterates a set, integration.py:1725-1729)."""
+        tr = tracer()
+        xs = [tr.var(i) for i in range(self._nvars)]
+        A = self.sde(t, *xs, **self._sde_args_at(t))
+        self._check_sde_values(A)
+        eqs = A if self._system else (A,)
+        ids = sorted(set().union(*[set(a.keys()) for a in eqs]))
+        roots = []
+        for a in eqs:
+            keys = [k for k in ids if k in a] if self._system else list(a.keys())
+            roots.append([(k, tr.lift(a[k])) for k in keys])
+        return tr, roots
+
+    def _milstein_nodes(self, tr, roots):
+        """((b*b')*0.5) per equation, b' = d b / d(own variable); None when the
+        diffusion does not depend on it (Milstein == Euler)."""
+        out, memo = [], {}
+        for i, r in enumerate(roots):
+            b = dict(r).get('dw')
+            if b is None:
+                out.append(None)
+                continue
+            db = diff(tr, b, i if self._system else 0, memo)
+            if isinstance(db, float) and db == 0.0:
+                out.append(None)
+            else:
+                out.append(tr.apply('mul', tr.apply('mul', b, tr.lift(db)), 0.5))
+        return out
+
+    def _traced_signature(self, tr, roots, mil):
+        return tr.signature(roots) + '|mil:' + ','.join(
+            'n' if m is None else str(m.id) for m in mil)
+
+    def _build(self, t0):
+        if getattr(self, '_jit', None) is not None:
+            return self._jit
+        from .integration import SDE
+        if type(self).let is not SDE.let:
+            raise NotImplementedError(
+                'a custom let() hook cannot run on the device: traced SDEs '
+                'store the working state (exponentiated when log=True)')
+        tr, roots = self._trace(t0)
+        milstein = self.method == 'milstein'
+        mil = self._milstein_nodes(tr, roots) if milstein else [None]*len(roots)
+        sig = self._traced_signature(tr, roots, mil)
+        nleaf = len(tr.leaves)
+        src = (self._codegen_system if self._system else self._codegen_single)(tr, roots, mil)
+        handle = _compile(engine_source() + PRELUDE + src, type(self).__name__)
+        self._jit = dict(handle=handle, sig=sig, nleaf=nleaf, milstein=milstein,
+                         source=src)
+        return self._jit
+
+    def _leaf_values(self, t):
+        """Re-trace at time t and return the leaf values (structure checked)."""
+        tr, roots = self._trace(t)
+        mil = (self._milstein_nodes(tr, roots) if self._jit['milstein']
+               else [None]*len(roots))
+        if self._traced_signature(tr, roots, mil) != self._jit['sig']:
+            raise NotImplementedError(
+                'the sde function takes a different computation path at t={}: '
+                'time-dependent control flow cannot be compiled'.format(t))
+        return [n.value for n in tr.leaves]
+
+    # ---- SDE lowering hooks -----------------------------------------------
+    def _spec(self):
+        lead, ncomp = self._lanes()
+        groups = int(np.prod(lead, dtype=int))
+        jit = self._build(0.)
+        return _engine.problem_spec(_lib.MODEL_JIT, ncomp, groups,
+                                    jit_handle=jit['handle']), lead
+
+    def _stats_centre(self, w0l):
+        w = w0l.mean(axis=-1)
+        return np.exp(w) if self.log else w
+
+    def _records(self, spec, seg, lead, replay):
+        jit = self._jit
+        dw, dj = self.sources.get('dw'), self.sources.get('dj')
+        lanes = self._param_target()
+        # is anything time-dependent?  (callable parameters, explicit use of t)
+        probe = [float(seg.s[0]), float(seg.s[-1])] if seg.n_steps else [0.]
+        vals = [self._leaf_values(s) for s in probe]
+        tdep = any(not np.array_equal(a, b) for a, b in zip(vals[0], vals[-1]))
+        tdep = tdep or any(callable(z) for z in
+                           self._get_args(self._sde_args_keys).values())
+        corr_t = not replay and isinstance(dw, wiener_source) and callable(dw.corr)
+        jumps_t = spec.jumps and not replay
+        n = seg.n_steps if (tdep or corr_t or jumps_t) and seg.n_steps else 1
+        rec = np.zeros((n, spec.groups, spec.npt))
+        per = jit['nleaf'] + (6 if spec.jumps else 0)
+        ncomp = self._rec_comps
+        for i in range(n):
+            s = seg.s[i] if seg.n_steps else 0.
+            ds = seg.ds[i] if seg.n_steps else 0.
+            leaves = vals[0] if (i == 0 or not tdep) else self._leaf_values(float(s))
+            cols = [lane_values(v, lanes, 'SDE parameter').reshape(spec.groups, ncomp)
+                    for v in leaves]
+            if spec.jumps:
+                zero = np.zeros((spec.groups, ncomp))
+                if replay:
+                    cols += [zero]*6
+                else:
+                    mid = s + ds/2
+                    lam = lane_values(dj.dn.lam_at(mid), lanes, 'lam').reshape(spec.groups, ncomp)
+                    lamdt = np.abs(ds)*lam
+                    kind, a, b, pa = dj.y.at(mid)
+                    cols += [lamdt, np.exp(-lamdt), zero + kind] + [
+                        lane_values(z, lanes, 'jump law parameter').reshape(spec.groups, ncomp)
+                        for z in (a, b, pa)]
+            if cols:
+                block = np.stack(cols, axis=-1)              # [G, ncomp, per]
+                rec[i, :, :spec.npc] = block.reshape(spec.groups, ncomp*per)
+            if spec.nchol:
+                L = None
+                if not replay and isinstance(dw, wiener_source):
+                    L = dw.chol_at(s + ds/2)
+                rec[i, :, spec.npc:] = _engine.chol_entries(L, spec.ndw)
+        return rec
+
+    # ---- code generation ----------------------------------------------------
+    def _codegen_single(self, tr, roots, mil):
+        lead, m = self._lanes()
+        ids = [k for k, _ in roots[0]]
+        unknown = set(ids) - {'dt', 'dw', 'dj'}
+        if unknown:
+            raise NotImplementedError('differentials {} have no device '
+                                      'implementation'.format(unknown))
+        jumps = 'dj' in self.sources
+        nleaf = len(tr.leaves)
+        per = nleaf + (6 if jumps else 0)
+        em = emitter(lambda k: 'p[%d*c + %d]' % (per, k), lambda i: 'x[c]')
+        terms = []
+        for k, nd in roots[0]:
+            dz = {'dt': 'ds', 'dw': 'dw[c]', 'dj': 'dj[c]'}[k]
+            terms.append('xmul(%s, %s)' % (em.ref(nd), dz))
+        inc = terms[0]
+        for tm in terms[1:]:
+            inc = 'xadd(%s, %s)' % (inc, tm)
+        body = list(em.lines)
+        em.lines = []
+        body.append('double xn = xadd(x[c], %s);' % inc)
+        if mil[0] is not None:
+            body += _flush(em, mil[0])
+            body.append('xn = xadd(xn, xmul(%s, xsub(xmul(dw[c], dw[c]), ds)));'
+                        % em.ref(mil[0]))
+        body.append('x[c] = xn;')
+        return _model_source(m, m, per*m, jumps, per, nleaf, body, self.log, loop=True)
+
+    def _codegen_system(self, tr, roots, mil):
+        q = self.q
+        if 'dj' in self.sources or 'dn' in self.sources:
+            raise NotImplementedError('jumps in traced systems of SDEs')
+        nleaf = len(tr.leaves)
+        em = emitter(lambda k: 'p[%d]' % k, lambda i: 'x[%d]' % i)
+        news = []
+        for i, r in enumerate(roots):
+            terms = []
+            for k, nd in r:
+                if k not in ('dt', 'dw'):
+                    raise NotImplementedError('differential ' + k)
+                dz = 'ds' if k == 'dt' else 'dw[%d]' % i
+                terms.append('xmul(%s, %s)' % (em.ref(nd), dz))
+            inc = terms[0] if terms else '0.0'
+            for tm in terms[1:]:
+                inc = 'xadd(%s, %s)' % (inc, tm)
+            news.append((i, inc))
+        body = list(em.lines)
+        em.lines = []
+        for i, inc in news:
+            body.append('double xn%d = xadd(x[%d], %s);' % (i, i, inc))
+        for i in range(q):
+            if mil[i] is not None:
+                body += _flush(em, mil[i])
+                body.append('xn%d = xadd(xn%d, xmul(%s, xsub(xmul(dw[%d], dw[%d]), ds)));'
+                            % (i, i, em.ref(mil[i]), i, i))
+        for i in range(q):
+            body.append('x[%d] = xn%d;' % (i, i))
+        return _model_source(q, q, nleaf, False, 0, 0, body, self.log, loop=False)
+
+
+def _flush(em, nd):
+    """Emit the statements needed for node nd (and return them)."""
+    before = len(em.lines)
+    em.ref(nd)
+    new = em.lines[before:]
+    del em.lines[before:]
+    return new
+
+
+def _model_source(nw, ndw, npc, jumps, jp_stride, jp_off, body, log, loop):
+    lines = ['namespace sdeb {', 'struct UserModel {',
+             '    enum { NW = %d, NDW = %d, NX = %d, NPC = %d, NCNT = %d, JUMPS = %d,'
+             % (nw, ndw, nw, npc, nw if jumps else 0, int(jumps)),
+             '           JP_STRIDE = %d, JP_OFF = %d };' % (jp_stride, jp_off),
+             '    static __device__ __forceinline__ void step(double (&x)[NW], const double* p,',
+             '            double ds, const double* dw, const double* dj, int (&cnt)[NCNT + 1]) {']
+    if loop:
+        lines.append('#pragma unroll')
+        lines.append('        for (int c = 0; c < NW; ++c) {')
+        lines += ['            ' + b for b in body]
+        lines.append('        }')
+    else:
+        lines += ['        ' + b for b in body]
+    lines += ['    }',
+              '    static __device__ __forceinline__ void emit(const double (&x)[NW], double (&v)[NX]) {',
+              '#pragma unroll',
+              '        for (int c = 0; c < NW; ++c) v[c] = %s;' % ('exp(x[c])' if log else 'x[c]'),
+              '    }', '};', '}',
+              'extern "C" __constant__ int sdeb_jit_dims[6] = {%d, %d, %d, %d, %d, %d};'
+              % (nw, ndw, nw, npc, nw if jumps else 0, int(jumps)),
+              'extern "C" __global__ void __launch_bounds__(SDEB_THREADS, 1)',
+              'sdeb_jit_entry(const sdeb::KArgs a) { sdeb::integrate_body<sdeb::UserModel, false>(a); }',
+              '']
+    return '\n'.join(lines)
+
+
+def evaluate(nd, xs, cache=None):
+    """Host interpreter of a DAG node (NumPy arithmetic, same rounding as the
+    emitted CUDA for + - * / sqrt max min): used by the CPU tests to check the
+    tracer and the symbolic derivative without a GPU."""
+    cache = {} if cache is None else cache
+    if nd.id in cache:
+        return cache[nd.id]
+    if nd.op == 'var':
+        r = xs[nd.index]
+    elif nd.op == 'leaf':
+        r = nd.value
+    else:
+        a = [evaluate(z, xs, cache) for z in nd.args]
+        f = {'add': np.add, 'sub': np.subtract, 'mul': np.multiply,
+             'div': np.divide, 'neg': np.negative, 'abs': np.abs,
+             'sqrt': np.sqrt, 'square': np.square, 'exp': np.exp, 'log': np.log,
+             'sin': np.sin, 'cos': np.cos, 'tanh': np.tanh, 'log1p': np.log1p,
+             'expm1': np.expm1, 'pow': np.power, 'max': np.maximum,
+             'min': np.minimum, 'sign': np.sign,
+             'ge': lambda u, v: (u >= v)*1., 'le': lambda u, v: (u <= v)*1.}[nd.op]
+        r = f(*a)
+    cache[nd.id] = r
+    return r

@@ -602,7 +602,7 @@ extern "C" int sdeb_jit_compile(const char* source, const char* model_type, int6
     if (r) return fail(SDEB_EJIT, std::string("nvrtcCreateProgram: ") + g_nvrtc.GetErrorString(r));
     const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17",
                           "-default-device"};
-    r = g_nvrtc.CompileProgram(prog, 3, opts);
+    r = g_nvrtc.CompileProgram(prog, 4, opts);
     size_t lsz = 0;
     g_nvrtc.GetProgramLogSize(prog, &lsz);
     std::string plog(lsz, 0);

@@ -17,7 +17,7 @@ default --, 'device' HBM-resident container, 'stats' fused statistics only),
 import numpy as np
 import torch
 
-from . import _cuda, _engine, _lib
+from . import _cuda, _engine, _jit, _lib
 from .infrastructure import (
     process, device_process, wiener_source, poisson_source, cpoisson_source,
     replay_source, norm_rv, double_exp_rv, lane_values, _law,
@@ -276,7 +276,7 @@ class path_stats:
 # SDE (reference integration.py:781-1581)
 # --------------------------------------------------------------------------
 
-class SDE:
+class SDE(_jit._traced):
     """A user- or preset-defined Ito SDE, cooperating with ``integrator``
     (which must follow in the MRO).  Same construction protocol as the
     reference ``SDE`` class; the equation runs on the GPU either through a
@@ -576,15 +576,8 @@ class SDE:
                 return src.next_key()
         return 0
 
-    def _records(self, spec, seg, lead, replay):
-        raise NotImplementedError
-
-    def _spec(self):
-        raise NotImplementedError
-
-    def _stats_centre(self, w0):
-        """Shift of the power sums: the emitted initial value."""
-        raise NotImplementedError
+    # _spec / _records / _stats_centre: generic traced lowering inherited from
+    # _jit._traced; the preset equations below override them.
 
     def _device_run(self, tt, grid):
         if self.method not in self._device_schemes:
@@ -647,6 +640,7 @@ class SDEs(SDE):
 
     q = 1
     addaxis = False
+    _system = True
 
     def _inspect_args_defaults(self):
         if self.q < 1:
@@ -712,8 +706,14 @@ class SDEs(SDE):
         return tuple(_wrap(tt, xx) for xx in self.unpack(XX))
 
     def _lanes(self):
-        # one lane owns the q (x N) stacked components of the last axis
-        return self.wshape[:-1], self.wshape[-1]
+        """Traced systems: one lane owns the q variables of an element of
+        vshape (the stacked last axis when addaxis=True, forced for
+        vshape=())."""
+        if not self.addaxis:
+            raise NotImplementedError(
+                'traced systems of SDEs need addaxis=True (or vshape=()): one '
+                'lane owns the q variables of an element of vshape')
+        return self.wshape[:-1], self.q
 
 
 # --------------------------------------------------------------------------
@@ -748,9 +748,7 @@ def _SDE_from_function(f, q=None, sources=None, log=False, addaxis=False):
                             "or 'sources'".format(f))
     flags = dict(q=neq, sources=ids, log=log, addaxis=addaxis,
                  sde=staticmethod(f))
-    from ._jit import traced_SDE, traced_SDEs
-    mixin = traced_SDE if base is SDE else traced_SDEs
-    return type('SDE_wrapper', (mixin,), flags)
+    return type('SDE_wrapper', (base,), flags)
 
 
 def integrate(sde=None, *, q=None, sources=None, log=False, addaxis=False):

@@ -168,3 +168,50 @@ def test_no_cpu_fallback():
     out = ctypes.c_double()
     rc = _lib.lib.sdeb_fp64_peak(10, ctypes.byref(out), None)
     assert rc != 0 and _lib.lib.sdeb_last_error()
+
+
+def test_tracer_and_symbolic_derivative():
+    from sdepy_b200 import _jit
+
+    def f(t, x, a=1.5, b=.3):
+        return {'dt': a*(b - x)/(1 + x**2), 'dw': np.sqrt(np.maximum(x, 0.))*np.exp(-b*x) + np.sin(x)*x}
+
+    P = sd.integrate(f)(paths=4, a=1.5, b=.3)
+    tr, roots = P._trace(0.)
+    x = np.array([.2, .7, 1.3, 2.])
+    got = {k: _jit.evaluate(n, [x]) for k, n in roots[0]}
+    want = f(0., x)
+    assert np.array_equal(got['dt'], want['dt']) and np.array_equal(got['dw'], want['dw'])
+    memo = {}
+    db = _jit.diff(tr, dict(roots[0])['dw'], 0, memo)
+    h = 1e-6
+    num = (f(0., x + h)['dw'] - f(0., x - h)['dw'])/(2*h)
+    assert np.allclose(_jit.evaluate(tr.lift(db), [x]), num, rtol=1e-6)
+    # structure is stable in time, leaf values are not
+    P2 = sd.integrate(f)(paths=4, a=lambda t: 1.5 + t, b=.3)
+    t0, r0 = P2._trace(0.)
+    t1, r1 = P2._trace(1.)
+    assert t0.signature(r0) == t1.signature(r1)
+    assert [float(l.value) for l in t0.leaves] != [float(l.value) for l in t1.leaves]
+
+
+def test_integrate_decorator_infers_equations_and_sources():
+    @sd.integrate
+    def one(t, x, k=1.):
+        return {'dt': -k*x, 'dw': 1.}
+    assert one.q == 0 and one.sources == {'dt', 'dw'}
+
+    # like the reference, a function of several variables cannot be probed by
+    # f() / f(1., 1.) unless its arguments have defaults (integration.py:1851-1859)
+    @sd.integrate
+    def two(t=0., x=1., y=1., k=1.):
+        return ({'dt': -k*x, 'dw': y}, {'dt': 0, 'dw': .1})
+    assert two.q == 2 and issubclass(two, sd.SDEs)
+    with pytest.raises(TypeError):
+        sd.integrate(lambda t, x, y: ({'dt': x}, {'dt': y}))
+    P = two(paths=3, x0=(1., 2.))
+    assert P.wshape == (2,) and P.addaxis
+    with pytest.raises(TypeError):
+        sd.integrate(lambda: 1/0)
+    with pytest.raises(TypeError):
+        sd.integrate(one.sde, q=3)
