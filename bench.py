@@ -62,7 +62,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--paths', type=float, default=1e8, help='paths per GPU')
-    ap.add_argument('--cpu-sample-paths', type=int, default=200_000)
+    ap.add_argument('--cpu-sample-paths', type=int, default=2_000_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
