@@ -84,9 +84,13 @@ static const int64_t kMaxStatsSmem = 96 * 1024;   // accumulators kept in smem u
 static int64_t smem_bytes(const ModelInfo& mi, const sdeb_problem* p, bool stats_in_kernel) {
     int64_t nch = mi.ndw > 1 ? (int64_t)mi.ndw * (mi.ndw + 1) / 2 : 0;
     int64_t npt = mi.npc + nch;
-    int64_t d = TAB_DOUBLES + 2 * STEP_CHUNK + (int64_t)STEP_CHUNK * npt + 8 * NSTAT * mi.nx;
+    // dynamic part only: tables and the staged step block are static __shared__
+    int64_t d = (int64_t)STEP_CHUNK * npt + 8 * NSTAT * mi.nx;
     if (stats_in_kernel) d += p->n_rows * p->n_groups * mi.nx * NSTAT;
-    return d * 8 + STEP_CHUNK * 4 + 16;
+    int64_t bytes = d * 8;
+    if (p->noise == SDEB_NOISE_REPLAY)       // cp.async ring of the replay table
+        bytes += (int64_t)replay_depth(mi.ndw) * mi.ndw * kThreads * 8;
+    return bytes;
 }
 
 // the lean kernel serves the hot configuration: Philox draws, one
@@ -128,7 +132,7 @@ static int plan_impl(const sdeb_problem* p, sdeb_plan_t* plan, ModelInfo& mi, bo
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) {
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
-        if (plan->smem_bytes > 48 * 1024)
+        if (plan->smem_bytes > 32 * 1024)   // + ~10 KB of static shared memory
             cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)plan->smem_bytes);
         int o = 0;
