@@ -1,0 +1,137 @@
+"""GPU edge cases the reference's own tests exercise (sdepy/tests/
+test_integrator.py:63-178, test_processes.py:443-596, test_source.py:164-284):
+degenerate timelines, single paths, ragged path counts, shapes, sources used
+stand-alone, cumulation of montecarlo updates."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sde_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def sd():
+    import sdepy_b200
+    return sdepy_b200
+
+
+def test_single_time_point_and_no_steps():
+    m = sd()
+    x = m.ornstein_uhlenbeck_process(paths=7, x0=3.)((0.5,))
+    assert x.shape == (1, 7) and np.array_equal(np.asarray(x), np.full((1, 7), 3.))
+    # steps=None: the timeline itself is the grid (integration.py:213-214)
+    P = m.wiener_process(paths=5, x0=1., mu=2., sigma=0.)
+    x = P((0., .25, 1.))
+    assert np.allclose(np.asarray(x), np.array([1., 1.5, 3.])[:, None])
+    assert P.info['computed_steps'] == 2 and P.info['stored_steps'] == 2
+    # integer timeline is integrated in float, returned as given (529-530, 584)
+    x = m.wiener_process(paths=3, x0=0., mu=1., sigma=0.)((0, 1, 2))
+    assert x.t.dtype.kind == 'i' and np.allclose(np.asarray(x)[:, 0], [0., 1., 2.])
+
+
+@pytest.mark.parametrize('paths', [1, 31, 32, 33, 255, 256, 257, 1000])
+def test_ragged_path_counts_replay(paths):
+    m = sd()
+    rng = np.random.default_rng(paths)
+    n = 70                      # crosses the 64-step staging block
+    grid = np.linspace(0., 2., n + 1)
+    dW = rng.standard_normal((n, paths))*np.sqrt(np.diff(grid))[:, None]
+    par = dict(theta=.3, k=1.2, sigma=.5)
+    out, _ = orc.euler_replay('ornstein_uhlenbeck', par, .1, grid, [0, 10, 64, 65, n], dW)
+    x = m.ornstein_uhlenbeck_process(paths=paths, steps=grid, x0=.1,
+                                     dw=m.replay_source(dW), **par)(grid[[0, 10, 64, 65, n]])
+    assert np.array_equal(np.asarray(x), out)
+
+
+def test_vshape_groups_and_per_component_parameters():
+    m = sd()
+    rng = np.random.default_rng(1)
+    paths, n = 50, 12
+    grid = np.linspace(0., 1., n + 1)
+    vshape = (2, 3)
+    dW = rng.standard_normal((n,) + vshape + (paths,))*np.sqrt(1/n)
+    mu = np.arange(6.).reshape(2, 3, 1)*.01
+    sigma = .1 + np.arange(6.).reshape(2, 3, 1)*.05
+    x0 = 1. + np.arange(3.).reshape(3, 1)
+    out, _ = orc.euler_replay('lognorm', dict(mu=mu, sigma=sigma), x0, grid, [0, n], dW)
+    x = m.lognorm_process(paths=paths, vshape=vshape, steps=grid, x0=x0, mu=mu,
+                          sigma=sigma, dw=m.replay_source(dW))((0., 1.))
+    assert x.shape == (2, 2, 3, paths)
+    assert np.abs(np.asarray(x)/out - 1).max() <= 4*np.finfo(float).eps
+    # philox: every (component, path) lane gets its own stream
+    y = np.asarray(m.lognorm_process(paths=2000, vshape=vshape, steps=20, x0=1., mu=0.,
+                                     sigma=.2, seed=3)((0., 1.)))[-1]
+    c = np.corrcoef(np.log(y).reshape(6, -1))
+    assert np.abs(c - np.eye(6)).max() < 5/np.sqrt(2000)
+
+
+def test_per_path_initial_condition():
+    m = sd()
+    rng = np.random.default_rng(2)
+    paths, n = 300, 8
+    grid = np.linspace(0., 1., n + 1)
+    dW = rng.standard_normal((n, paths))*np.sqrt(1/n)
+    x0 = 1. + rng.random(paths)
+    out, _ = orc.euler_replay('ornstein_uhlenbeck', dict(theta=0., k=1., sigma=1.), x0,
+                              grid, [0, n], dW)
+    x = m.ornstein_uhlenbeck_process(paths=paths, steps=grid, x0=x0,
+                                     dw=m.replay_source(dW))((0., 1.))
+    assert np.array_equal(np.asarray(x), out)
+
+
+def test_standalone_sources():
+    m = sd()
+    dw = m.wiener_source(paths=200_000, vshape=(2,), rho=.6, seed=1)
+    z = dw(0., .25)
+    assert z.shape == (2, 200_000)
+    assert abs(z.var() - .25) < .25*5*np.sqrt(2/z.size)
+    assert abs(np.corrcoef(z)[0, 1] - .6) < 5/np.sqrt(200_000)
+    assert not np.array_equal(z, dw(0., .25))            # the stream advances
+    z2 = m.wiener_source(paths=200_000, vshape=(2,), rho=.6, seed=1)(0., .25)
+    assert np.array_equal(z, z2)                          # same seed, same draw
+    # cpoisson with a (numerically) constant jump size: dj == dn * value
+    # (sdepy/tests/test_source.py:257-269)
+    dj = m.cpoisson_source(paths=100_000, lam=3., y=m.uniform_rv(a=.7, b=.7), seed=2)
+    j = dj(0., 1.)
+    assert np.allclose(j, dj.dn_value*.7, rtol=1e-14)
+    assert abs(dj.dn_value.mean() - 3.) < 5*np.sqrt(3/100_000)
+    dn = m.poisson_source(paths=100_000, lam=.5, seed=4)(0., -2.)
+    assert (dn <= 0).all() and abs(dn.mean() + 1.) < 5*np.sqrt(1/100_000)
+
+
+def test_outputs_agree_across_modes():
+    m = sd()
+    kw = dict(paths=5000, steps=30, x0=100., y0=.04, mu=.03, sigma=1., theta=.04, k=2.,
+              xi=.5, rho=-.6, seed=77)
+    xh, yh = m.full_heston_process(**kw)((0., .5, 1.))
+    xd, yd = m.full_heston_process(output='device', **kw)((0., .5, 1.))
+    assert isinstance(xd, m.device_process) and xd.shape == xh.shape
+    assert np.array_equal(np.asarray(xd), np.asarray(xh))
+    assert np.array_equal(np.asarray(yd.cpu()), np.asarray(yh))
+    st = m.full_heston_process(output='stats', **kw)((0., .5, 1.))
+    assert np.allclose(np.asarray(st.pmean())[:, 0, 0], np.asarray(xh).mean(axis=-1), rtol=1e-12)
+    assert np.allclose(np.asarray(st.pmean())[:, 1, 0], np.asarray(yh).mean(axis=-1), rtol=1e-12)
+    assert np.allclose(np.asarray(st.pstd())[:, 1, 0], np.asarray(yh).std(axis=-1), rtol=1e-10)
+    # getinfo=False: no diagnostics, same paths
+    P = m.full_heston_process(getinfo=False, **kw)
+    x2, _ = P((0., .5, 1.))
+    assert np.array_equal(np.asarray(x2), np.asarray(xh)) and 'negative_y_count' not in P.info
+
+
+def test_reference_style_generic_source_objects():
+    """A source written against the reference's protocol only (callable with
+    paths/vshape) drives the kernel through host evaluation + replay."""
+    m = sd()
+
+    class lattice:
+        paths, vshape = 64, ()
+
+        def __call__(self, t, dt):
+            k = np.arange(64)
+            return np.sqrt(abs(dt))*np.where((k + int(round(t*8))) % 2, 1., -1.)
+
+    x = m.wiener_process(paths=64, steps=9, dw=lattice())((0., 1.))
+    grid = np.linspace(0, 1, 9)
+    want = sum(lattice()(t, grid[1] - grid[0]) for t in grid[:-1])
+    assert np.allclose(np.asarray(x)[-1], want, rtol=1e-14, atol=1e-15)
