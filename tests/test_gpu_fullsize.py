@@ -1,0 +1,123 @@
+"""BASELINE.json configurations at FULL size on the GPU, checked through
+size-independent properties (the oracle cannot run these sizes in seconds):
+additivity of shard statistics, discrete-Euler moment recursions, closed forms
+within standard errors, dump -> replay idempotence, histogram conservation."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HESTON = dict(x0=100., mu=.03, sigma=1., y0=.04, theta=.04, k=2., xi=.3, rho=-.7)
+
+
+def sd():
+    import sdepy_b200
+    return sdepy_b200
+
+
+def test_config3_heston_1e8_terminal_stats_and_shard_additivity():
+    m = sd()
+    from sdepy_b200 import _lib
+    paths = 100_000_000
+    grid = np.linspace(0., 1., 253)
+    pay = ('call', 100., float(np.exp(-.03)))
+    kw = dict(steps=grid, seed=2024, output='stats', payoff=pay, getinfo=False, **HESTON)
+    full = m.heston_process(paths=paths, **kw)((0., 1.))
+    price = float(np.asarray(full.payoff_mean())[-1, 0])
+    err = float(np.asarray(full.payoff_stderr())[-1, 0])
+    # closed form 9.2425 (Gil-Pelaez on sdepy.analytical.heston_log_chf); the
+    # Euler/full-truncation bias at dt = 1/252 is ~3e-3 (reference at 1e6
+    # paths: 9.2335 +/- 0.0116)
+    assert err < 2e-3 and abs(price - 9.2425) < 4*err + 1e-2
+    mean = float(np.asarray(full.pmean())[-1, 0])
+    assert abs(mean - 100*np.exp(.03)) < 5*float(np.asarray(full.stderr())[-1, 0])
+    # the same global paths integrated as 3 uneven shards: sums add up
+    parts, off = [], 0
+    for n in (40_000_000, 35_000_001, 24_999_999):
+        parts.append(m.heston_process(paths=n, path_offset=off, **kw)((0., 1.)))
+        off += n
+    s = sum(p.sums for p in parts)
+    for k in (0, 1, 2, 3, 6, 7):
+        assert np.allclose(s[..., k], full.sums[..., k], rtol=1e-10, atol=1e-6)
+    assert np.array_equal(np.min([p.sums[..., 4] for p in parts], axis=0), full.sums[..., 4])
+    assert np.array_equal(np.max([p.sums[..., 5] for p in parts], axis=0), full.sums[..., 5])
+
+
+def test_config2_ou_hw_1e6_full_path():
+    m = sd()
+    paths, n = 1_000_000, 500
+    tl = np.linspace(0., 5., n + 1)
+    x = m.ornstein_uhlenbeck_process(x0=.1, theta=lambda t: .2 + .1*t, k=1., sigma=.3,
+                                     paths=paths, seed=9, output='device')(tl)
+    assert x.shape == (n + 1, paths)
+    mean = np.asarray(x.pmean())[:, 0]
+    var = np.asarray(x.pvar())[:, 0]
+    mm, vv, want_m, want_v = .1, 0., [.1], [0.]
+    for i in range(n):          # exact moments of the discrete Euler recursion
+        dt = tl[i + 1] - tl[i]
+        mm, vv = mm + 1.*((.2 + .1*tl[i]) - mm)*dt, (1 - dt)**2*vv + .09*dt
+        want_m.append(mm); want_v.append(vv)
+    want_m, want_v = np.array(want_m), np.array(want_v)
+    assert np.abs(mean[1:] - want_m[1:]).max() < 5*np.sqrt(want_v.max()/paths)
+    assert np.abs(var[1:]/want_v[1:] - 1).max() < 6*np.sqrt(2/paths)
+    assert torch.isfinite(x.x).all()
+    from tests.cases import HW
+    h = m.hull_white_process(paths=paths, seed=10, output='device', **HW)(tl)
+    assert h.shape == (n + 1, paths) and torch.isfinite(h.x).all()
+    hm = np.asarray(h.pmean())[:, 0]
+    # factor means follow m <- m + k(theta - m)dt; only factor 0 has a non-zero mean
+    f0, want = .01, [.01]
+    for i in range(n):
+        f0 = f0 + .1*((.02 + .001*tl[i]) - f0)*(tl[i + 1] - tl[i])
+        want.append(f0)
+    hv = float(np.asarray(h.pvar())[-1, 0])
+    assert np.abs(hm - np.array(want)).max() < 5*np.sqrt(hv/paths)
+
+
+def test_config4_jumps_replay_idempotence_chunk():
+    """One 1e6-path chunk of the 1e7 x 1000 Merton config: dump the Philox
+    increments, replay them, compare paths and jump counts bit for bit."""
+    m = sd()
+    paths, n = 1_000_000, 1000
+    kw = dict(x0=1., mu=.05, sigma=.2)
+    P = m.merton_jumpdiff_process(paths=paths, steps=n + 1, lam=2., a=-.1, b=.15, seed=11,
+                                  output='device', **kw)
+    P._dump_increments = True
+    x = P((0., 1.))
+    d = P._last_run.dump[0]
+    jc = P.info['jump_count']
+    assert abs(float(jc.double().mean()) - 2.) < 5*np.sqrt(2/paths)
+    R = m.merton_jumpdiff_process(
+        paths=paths, steps=n + 1, output='device',
+        dw=m.replay_source(d['dW'].reshape(n, paths)),
+        dj=m.replay_source(d['dJ'].reshape(n, paths), dn=d['dN'].reshape(n, paths)), **kw)
+    xr = R((0., 1.))
+    assert torch.equal(xr.x, x.x)
+    assert torch.equal(R.info['jump_count'], jc)
+    assert torch.equal(d['dN'].sum(dim=0).reshape(-1), jc.reshape(-1))
+    assert np.allclose(R.info['jump_rate'], P.info['jump_rate'], rtol=1e-13)
+
+
+def test_config5_milstein_1e8_montecarlo():
+    m = sd()
+
+    @m.integrate
+    def f(t, x, mu=.05, sigma=.2):
+        return {'dt': mu*x, 'dw': sigma*x}
+
+    paths = 100_000_000
+    x = f(paths=paths, steps=2001, x0=1., method='milstein', seed=12, output='device',
+          getinfo=False)((0., 1.))
+    a = m.montecarlo(bins=100)
+    for k in range(4):                      # cumulate in 4 chunks
+        a.update(x.x[-1, k*paths//4:(k + 1)*paths//4])
+    assert a.paths == paths
+    counts, edges = a.histogram()
+    assert counts.sum() + a.outpaths == paths
+    assert abs(float(a.mean()) - np.exp(.05)) < 4*float(a.stderr())
+    sdv = np.exp(.05)*np.sqrt(np.exp(.04) - 1)
+    assert abs(float(a.std())/sdv - 1) < 1e-3
+    one = m.montecarlo(x.x[-1], bins=edges)
+    assert np.array_equal(one.histogram()[0], counts)
+    assert np.allclose(one.mean(), a.mean(), rtol=1e-12)
