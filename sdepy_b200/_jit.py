@@ -304,6 +304,35 @@ def _compile(source, name):
     return handle.value
 
 
+PRESET_FUNCTORS = {
+    _lib.MODEL_LINEAR: 'LinearSDE<%d, false, false>',
+    _lib.MODEL_LINEAR_LOG: 'LinearSDE<%d, true, false>',
+    _lib.MODEL_JUMPDIFF: 'LinearSDE<%d, true, true>',
+    _lib.MODEL_MEANREV: 'MeanRevertingSDE<%d, false>',
+    _lib.MODEL_HULL_WHITE: 'MeanRevertingSDE<%d, true>',
+    _lib.MODEL_CIR: 'CoxIngersollRossSDE<%d>',
+    _lib.MODEL_HESTON: 'HestonSDE<%d, false>',
+    _lib.MODEL_HESTON_FULL: 'HestonSDE<%d, true>',
+}
+
+
+def instantiate_preset(model, ncomp):
+    """NVRTC instantiation of a hand-written preset functor for a component
+    count that is not pre-compiled into libsdeb.so (e.g. a 7-factor
+    Hull-White).  Same engine, same functor source -- only the template
+    argument differs."""
+    functor = PRESET_FUNCTORS[model] % ncomp
+    src = '\n'.join([
+        'namespace sdeb { typedef %s UserModel; }' % functor,
+        'extern "C" __constant__ int sdeb_jit_dims[6] = {',
+        '    sdeb::UserModel::NW, sdeb::UserModel::NDW, sdeb::UserModel::NX,',
+        '    sdeb::UserModel::NPC, sdeb::UserModel::NCNT, sdeb::UserModel::JUMPS};',
+        'extern "C" __global__ void __launch_bounds__(SDEB_THREADS, 1)',
+        'sdeb_jit_entry(const sdeb::KArgs a) { sdeb::integrate_body<sdeb::UserModel, false>(a); }',
+        ''])
+    return _compile(engine_source() + src, 'preset_%d_%d' % (model, ncomp))
+
+
 def engine_source():
     with open(os.path.join(HERE, 'csrc', 'sde_engine.cuh')) as f:
         return f.read()

@@ -783,7 +783,14 @@ class _preset_SDE(SDE):
     def _spec(self):
         lead, ncomp = self._lanes()
         groups = int(np.prod(lead, dtype=int))
-        return _engine.problem_spec(self._model, ncomp, groups), lead
+        try:
+            return _engine.problem_spec(self._model, ncomp, groups), lead
+        except _lib.SdebError:
+            # component count not pre-instantiated in libsdeb.so: instantiate
+            # the same hand-written functor with NVRTC
+            handle = _jit.instantiate_preset(self._model, ncomp)
+            return _engine.problem_spec(_lib.MODEL_JIT, ncomp, groups,
+                                        jit_handle=handle), lead
 
     def _coeffs(self, p):
         """Per-component parameter tuple from the evaluated sde args, in the

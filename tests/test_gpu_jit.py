@@ -150,3 +150,29 @@ def test_untraceable_functions_fail_loudly():
 
     with pytest.raises(TypeError):
         branchy(paths=10, steps=5)((0., 1.))
+
+
+def test_preset_component_counts_beyond_the_precompiled_ones():
+    """7-factor Hull-White with a correlation matrix: not in libsdeb.so, the
+    same functor is instantiated by NVRTC.  Replay vs the oracle, bit-exact."""
+    m = sd()
+    rng = np.random.default_rng(3)
+    F, paths, n = 7, 120, 15
+    grid = np.linspace(0., 1., n + 1)
+    dW = rng.standard_normal((n, F, paths))*np.sqrt(1/n)
+    k = (.1 + .2*np.arange(F)).reshape(F, 1)
+    sigma = (.01 + .002*np.arange(F)).reshape(F, 1)
+    x0 = (.01*np.arange(F)).reshape(F, 1)
+    out, _ = orc.euler_replay('hull_white', dict(theta=.02, k=k, sigma=sigma), x0, grid,
+                              [0, 5, n], dW)
+    x = m.hull_white_process(paths=paths, factors=F, steps=grid, x0=x0, theta=.02, k=k,
+                             sigma=sigma, dw=m.replay_source(dW))(grid[[0, 5, n]])
+    assert np.array_equal(np.asarray(x), out)
+    # philox with a 7x7 correlation
+    c = .3*np.ones((F, F)) + .7*np.eye(F)
+    P = m.hull_white_process(paths=50_000, factors=F, steps=5, x0=x0, theta=.02, k=k,
+                             sigma=sigma, corr=c, seed=1)
+    P._dump_increments = True
+    P((0., 1.))
+    z = P._last_run.dump[0]['dW'].cpu().numpy()[0]
+    assert np.abs(np.corrcoef(z) - c).max() < 5/np.sqrt(50_000)

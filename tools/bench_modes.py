@@ -116,6 +116,12 @@ def main():
                                             dw=sd.replay_source(dW), steps=n + 1,
                                             output='device')((0., 1.)))
     rec('replay lognorm terminal only', p, n, t, stored=2*p, read=p*n)
+    del x
+    # non-log model: no exp at the store, pure stream (read 8 B + write 8 B per path-step)
+    t, x = timed(lambda: sd.ornstein_uhlenbeck_process(
+        x0=.1, theta=.2, k=1., sigma=.3, paths=p, dw=sd.replay_source(dW),
+        output='device')(tl))
+    rec('replay OU full path', p, n, t, stored=p*(n + 1), read=p*n)
     del x, dW
     # philox lognorm terminal (cheapest model: RNG-bound)
     p, n = int(100_000_000*a.scale), 250
