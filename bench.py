@@ -52,7 +52,7 @@ STRIKE, RATE = 100., .03
 # FP64-pipe warp-instructions executed per Heston path-step on the Philox /
 # no-store path of integrate_kernel<HestonSDE<1,false>> (DFMA+DMUL+DADD+DSETP
 # in the SASS between the step-loop head and the store check)
-N64_PER_PATH_STEP = 56
+N64_PER_PATH_STEP = 53
 
 
 def parse():
