@@ -116,6 +116,11 @@ typedef struct sdeb_problem {
     void* workspace;          /* >= plan.workspace_bytes when stats != NULL     */
     int64_t workspace_bytes;
     int64_t max_blocks;       /* 0 = auto (persistent grid, multiple of SM count) */
+    int64_t anti_dw_half;     /* K > 0: global paths p >= K reuse the Wiener stream of
+                                 p - K with the sign reversed (odd_wiener_source,
+                                 infrastructure.py:2095-2110); 0 = off          */
+    int64_t anti_dj_half;     /* K > 0: paths p >= K repeat the jumps of p - K
+                                 (even_cpoisson_source, 2133-2150); 0 = off     */
 } sdeb_problem;
 
 typedef struct sdeb_plan_t {
@@ -160,6 +165,13 @@ int64_t sdeb_moments_workspace(int64_t n_rows);
 int sdeb_moments(const double* x, int64_t n_rows, int64_t n_paths, int64_t pitch,
                  const double* centre /* [n_rows] device, may be NULL = 0 */,
                  double* stats, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Antithetic halves: out[r][k] = (x[r][k] + sign*x[r][half+k])/2, sign = +1 ('even')
+ * or -1 ('odd') -- montecarlo(use=...), infrastructure.py:2905-2914.
+ */
+int sdeb_antithetic_fold(const double* x, int64_t n_rows, int64_t half, int64_t pitch_in,
+                         int64_t pitch_out, int64_t sign, double* out, void* stream);
 
 /*
  * 1-D histogram of x[n] on given edges[nbins+1] with numpy.histogram

@@ -1,6 +1,6 @@
 """Build libsdeb.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
 
-    python -m sdepy_b200._build [--force]
+    python sdepy_b200/_build.py [--force]      (or __graft_entry__.build())
 
 nvcc cross-compiles without a GPU.  The built library lives next to its
 sources (sdepy_b200/csrc/libsdeb.so): git-ignored, but shipped to the GPU box.

@@ -82,7 +82,8 @@ class run_result:
 
 def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
         dev=None, replay=None, want_out=True, want_stats=False, centre=None,
-        payoff=None, counters=False, dn_sums=False, dump=False, max_blocks=0):
+        payoff=None, counters=False, dn_sums=False, dump=False, max_blocks=0,
+        anti_dw_half=0, anti_dj_half=0):
     """Run all segments.  ``records[k]`` is the parameter table of segment k,
     shaped [1 or n_steps, groups, npt]; ``replay`` (optional) is a list of
     dicts with device/host tables 'dW', 'dJ', 'dN' per segment.
@@ -179,6 +180,7 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
                 p.dJ_dump, p.dN_dump = d['dJ'].data_ptr(), d['dN'].data_ptr()
             res.dump.append(d)
         p.max_blocks = max_blocks
+        p.anti_dw_half, p.anti_dj_half = int(anti_dw_half), int(anti_dj_half)
         seg_stats = None
         if want_stats:
             p.centre = centre_d.data_ptr()

@@ -38,6 +38,7 @@ class Problem(C.Structure):
         ('counter', ptr), ('dn_sum', ptr), ('dW_dump', ptr),
         ('dJ_dump', ptr), ('dN_dump', ptr),
         ('workspace', ptr), ('workspace_bytes', i64), ('max_blocks', i64),
+        ('anti_dw_half', i64), ('anti_dj_half', i64),
     ]
 
 
@@ -56,7 +57,7 @@ def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             'sdepy_b200: the CUDA library %s is missing. Build it with '
-            '`python -m sdepy_b200._build` (needs nvcc); there is no CPU '
+            '`python sdepy_b200/_build.py` (needs nvcc); there is no CPU '
             'fallback.' % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     lib.sdeb_last_error.restype = C.c_char_p
@@ -68,6 +69,7 @@ def _load():
     lib.sdeb_integrate.argtypes = [C.POINTER(Problem), ptr]
     lib.sdeb_moments.argtypes = [ptr, i64, i64, i64, ptr, ptr, ptr, i64, ptr]
     lib.sdeb_histogram.argtypes = [ptr, i64, ptr, i64, i64, ptr, ptr, ptr]
+    lib.sdeb_antithetic_fold.argtypes = [ptr, i64, i64, i64, i64, i64, ptr, ptr]
     lib.sdeb_draw_wiener.argtypes = [ptr, i64, i64, i64, i64, i64, u64, i64,
                                      f64, ptr, ptr]
     lib.sdeb_draw_cpoisson.argtypes = [ptr, ptr, i64, i64, i64, i64, u64, i64,
@@ -87,7 +89,7 @@ lib = _load()
 
 EXPORTS = ('sdeb_abi_version', 'sdeb_last_error', 'sdeb_device_info',
            'sdeb_plan', 'sdeb_integrate', 'sdeb_moments_workspace',
-           'sdeb_moments', 'sdeb_histogram', 'sdeb_draw_wiener',
+           'sdeb_moments', 'sdeb_histogram', 'sdeb_antithetic_fold', 'sdeb_draw_wiener',
            'sdeb_draw_cpoisson', 'sdeb_test_normals', 'sdeb_test_philox',
            'sdeb_fp64_peak', 'sdeb_jit_compile', 'sdeb_jit_release')
 

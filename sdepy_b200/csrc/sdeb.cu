@@ -97,7 +97,8 @@ static int64_t smem_bytes(const ModelInfo& mi, const sdeb_problem* p, bool stats
 // time-invariant parameter record (passed through the constant bank), no dump
 static bool use_lean(const sdeb_problem* p, const ModelInfo& mi) {
     return mi.fn_lean && p->noise == SDEB_NOISE_PHILOX && p->params_host &&
-           p->n_psteps == 1 && p->n_groups == 1 && !p->dW_dump && !p->dJ_dump && !p->dN_dump;
+           p->n_psteps == 1 && p->n_groups == 1 && !p->dW_dump && !p->dJ_dump && !p->dN_dump &&
+           !p->anti_dw_half && !p->anti_dj_half;
 }
 
 static int plan_impl(const sdeb_problem* p, sdeb_plan_t* plan, ModelInfo& mi, bool need_device) {
@@ -214,6 +215,7 @@ extern "C" int sdeb_integrate(const sdeb_problem* p, void* stream_) {
     a.out = p->out; a.partials = p->stats ? (double*)p->workspace : NULL;
     a.centre = p->centre; a.counter = (i64*)p->counter; a.dn_sum = (i64*)p->dn_sum;
     a.dW_dump = p->dW_dump; a.dJ_dump = p->dJ_dump; a.dN_dump = (i64*)p->dN_dump;
+    a.anti_dw_half = p->anti_dw_half; a.anti_dj_half = p->anti_dj_half;
 
     void* args[] = {&a};
     CUDA_TRY(cudaLaunchKernel(lean ? mi.fn_lean : mi.fn, dim3((unsigned)plan.blocks), dim3(kThreads), args,
@@ -297,6 +299,35 @@ extern "C" int sdeb_moments(const double* x, int64_t n_rows, int64_t n_paths, in
     int64_t len = n_rows * NSTAT;
     fold_partials_kernel<<<(unsigned)((len + 127) / 128), 128, 0, stream>>>(
         (const double*)workspace, blocks, len, stats);
+    CUDA_TRY(cudaGetLastError());
+    return SDEB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// antithetic fold: out[r][k] = (x[r][k] + sign * x[r][half + k]) / 2
+// (montecarlo(use='even'|'odd'), infrastructure.py:2905-2914)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+antithetic_fold_kernel(const double* x, int64_t half, int64_t pitch_in, int64_t pitch_out,
+                       double sign, double* out) {
+    const int row = blockIdx.y;
+    const double* xr = x + (int64_t)row * pitch_in;
+    double* o = out + (int64_t)row * pitch_out;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < half;
+         i += (int64_t)gridDim.x * blockDim.x)
+        o[i] = __ddiv_rn(__dadd_rn(xr[i], __dmul_rn(sign, xr[half + i])), 2.0);
+}
+
+extern "C" int sdeb_antithetic_fold(const double* x, int64_t n_rows, int64_t half,
+                                    int64_t pitch_in, int64_t pitch_out, int64_t sign,
+                                    double* out, void* stream_) {
+    if (!x || !out || n_rows < 1 || n_rows > 65535 || half < 1 || pitch_in < 2 * half ||
+        pitch_out < half || (sign != 1 && sign != -1))
+        return fail(SDEB_EINVAL, "sdeb_antithetic_fold: bad arguments");
+    int64_t need = (half + 255) / 256;
+    int blocks = (int)(need < 1184 ? need : 1184);
+    antithetic_fold_kernel<<<dim3(blocks, (unsigned)n_rows), 256, 0, (cudaStream_t)stream_>>>(
+        x, half, pitch_in, pitch_out, (double)sign, out);
     CUDA_TRY(cudaGetLastError());
     return SDEB_OK;
 }

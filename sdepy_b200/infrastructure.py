@@ -661,6 +661,73 @@ def _draw_cpoisson(src, dn_src, law, t, dt, want_dj):
     return dj_h, dn_h
 
 
+# ---- antithetic variants (reference infrastructure.py:2047-2150) ---------
+
+def _check_even(paths):
+    if paths % 2:
+        raise ValueError('the number of paths for sources with antithetics '
+                         'should be even, not {}'.format(paths))
+
+
+class odd_wiener_source(wiener_source):
+    """dw with antithetic paths: the trailing K = paths/2 paths repeat the
+    leading K with the sign reversed (reference infrastructure.py:2095-2110).
+    In-kernel the second half reuses the Philox stream of path p - K."""
+    antithetic = True
+
+    def __init__(self, *, paths=2, **kw):
+        _check_even(paths)
+        super().__init__(paths=paths, **kw)
+
+    def __call__(self, t, dt):
+        self.paths //= 2
+        try:
+            z = super().__call__(t, dt)
+        finally:
+            self.paths *= 2
+        return np.concatenate((z, -z), axis=-1)
+
+
+class even_poisson_source(poisson_source):
+    """dn with antithetic paths exposing identical increments (reference
+    infrastructure.py:2113-2130)."""
+    antithetic = True
+
+    def __init__(self, *, paths=2, **kw):
+        _check_even(paths)
+        super().__init__(paths=paths, **kw)
+
+    def __call__(self, t, dt):
+        self.paths //= 2
+        try:
+            z = super().__call__(t, dt)
+        finally:
+            self.paths *= 2
+        return np.concatenate((z, z), axis=-1)
+
+
+class even_cpoisson_source(cpoisson_source):
+    """dj with antithetic paths exposing identical jumps (reference
+    infrastructure.py:2133-2150).  Like the reference's wrapper it does not
+    expose ``dn_value``."""
+    antithetic = True
+
+    def __init__(self, *, paths=2, **kw):
+        _check_even(paths)
+        super().__init__(paths=paths, **kw)
+
+    def __call__(self, t, dt):
+        self.paths //= 2
+        self.dn.paths //= 2
+        try:
+            z = super().__call__(t, dt)
+        finally:
+            self.paths *= 2
+            self.dn.paths *= 2
+        del self.dn_value
+        return np.concatenate((z, z), axis=-1)
+
+
 class replay_source:
     """Replay-mode source: a table of pre-drawn increments, one entry per
     integration step, e.g. the increments logged from the reference's own
@@ -743,10 +810,26 @@ class montecarlo:
         if self._use not in ('all', 'even', 'odd'):
             raise ValueError("use must be one of 'all', 'even', 'odd', not {}"
                              .format(self._use))
-        if self._use != 'all':
-            raise NotImplementedError(
-                "antithetic use='even'/'odd' is outside the accelerated path")
         x = self._as_device(sample, axis)
+        if self._use != 'all':
+            # half-sum / half-difference of antithetic pairs x[k], x[K+k]
+            # (reference infrastructure.py:2905-2914)
+            if x.shape[-1] % 2:
+                raise ValueError(
+                    'the sample axis for even or odd antithetics sampling '
+                    'should be of even length, but {} was found'
+                    .format(x.shape[-1]))
+            half = x.shape[-1]//2
+            rows_in = x.reshape(-1, x.shape[-1])
+            folded = _cuda.empty((rows_in.shape[0], half), x.device)
+            with torch.cuda.device(x.device):
+                for r0 in range(0, rows_in.shape[0], 32768):
+                    r1 = min(rows_in.shape[0], r0 + 32768)
+                    _lib.check(_lib.lib.sdeb_antithetic_fold(
+                        _cuda.ptr(rows_in[r0:r1]), r1 - r0, half, 2*half, half,
+                        1 if self._use == 'even' else -1, _cuda.ptr(folded[r0:r1]),
+                        _cuda.stream_ptr(x.device)))
+            x = folded.reshape(tuple(x.shape[:-1]) + (half,))
         vshape, m = tuple(x.shape[:-1]), x.shape[-1]
         rows = x.reshape(-1, m)
         first = self.paths == 0

@@ -20,6 +20,7 @@ import torch
 from . import _cuda, _engine, _jit, _lib
 from .infrastructure import (
     process, device_process, wiener_source, poisson_source, cpoisson_source,
+    odd_wiener_source, even_cpoisson_source,
     replay_source, norm_rv, double_exp_rv, lane_values, _law,
     _shape_setup, _const_param_setup, _variable_param_setup, _source_setup,
     _get_default_rng, _signature, _empty)
@@ -515,8 +516,9 @@ class SDE(_jit._traced):
         if unknown:
             raise NotImplementedError(
                 'sources {} have no device implementation'.format(unknown))
-        philox_ok = (dw is None or type(dw) is wiener_source) and (
-            dj is None or (type(dj) is cpoisson_source and dj.device_ready()))
+        philox_ok = (dw is None or type(dw) in (wiener_source, odd_wiener_source)) and (
+            dj is None or (type(dj) in (cpoisson_source, even_cpoisson_source)
+                           and dj.device_ready()))
         if philox_ok:
             return None
         tables = []
@@ -599,13 +601,23 @@ class SDE(_jit._traced):
         want_stats = self.output == 'stats'
         centre = self._stats_centre(w0l) if want_stats else None
         jumps = spec.jumps
+        anti = {}
+        if replay is None:
+            for key, src in (('anti_dw_half', self.sources.get('dw')),
+                             ('anti_dj_half', self.sources.get('dj'))):
+                if getattr(src, 'antithetic', False):
+                    if self.path_offset:
+                        raise NotImplementedError(
+                            'antithetic sources pair paths k and K+k of ONE '
+                            'launch: they cannot be combined with path_offset')
+                    anti[key] = self.paths//2
         res = _engine.run(
             spec, segs, tt.size, records, w0_arg, paths=self.paths,
             path_offset=self.path_offset, seed=self._philox_key(),
             dev=self.device, replay=replay, want_out=not want_stats,
             want_stats=want_stats, centre=centre, payoff=self.payoff,
             counters=self.getinfo, dn_sums=self.getinfo and jumps,
-            dump=getattr(self, '_dump_increments', False))
+            dump=getattr(self, '_dump_increments', False), **anti)
         if self.getinfo:
             self.info['computed_steps'] = int(sum(s.n_steps for s in segs))
             self.info['stored_steps'] = int(sum((s.store_row >= 0).sum() for s in segs))
@@ -1051,6 +1063,8 @@ class jumpdiff_SDE(_preset_SDE):
         """jump_count / jump_rate (reference 2588-2623).  In replay mode they
         are only available when the dj source exposes ``dn_value`` (2615)."""
         have_dn = replay is None or all('dN' in tab for tab in replay)
+        if replay is None and isinstance(self.sources.get('dj'), even_cpoisson_source):
+            have_dn = False      # the reference's antithetic wrapper hides dn_value
         if not have_dn:
             return
         if res.counter is not None:

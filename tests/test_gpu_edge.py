@@ -135,3 +135,45 @@ def test_reference_style_generic_source_objects():
     grid = np.linspace(0, 1, 9)
     want = sum(lattice()(t, grid[1] - grid[0]) for t in grid[:-1])
     assert np.allclose(np.asarray(x)[-1], want, rtol=1e-14, atol=1e-15)
+
+
+def test_antithetic_sources_and_montecarlo_use():
+    """odd_wiener_source / even_cpoisson_source (reference infrastructure.py:
+    2047-2150) and montecarlo(use='even'|'odd') (2905-2914)."""
+    m = sd()
+    K = 20_000
+    P = m.wiener_process(paths=2*K, steps=20, x0=0., mu=0., sigma=1.,
+                         dw=m.odd_wiener_source, seed=3)
+    x = np.asarray(P((0., 1.)))[-1]
+    assert np.array_equal(x[:K], -x[K:])                 # mirrored Brownian paths
+    assert abs(x[:K].var() - 1.) < 5*np.sqrt(2/K)
+    z = m.odd_wiener_source(paths=10, seed=1)(0., 1.)
+    assert z.shape == (10,) and np.array_equal(z[:5], -z[5:])
+    with pytest.raises(ValueError):
+        m.odd_wiener_source(paths=7)
+    # jump diffusion: opposite diffusion, identical jumps
+    J = m.merton_jumpdiff_process(paths=2*K, steps=50, x0=1., mu=0., sigma=.2, lam=3.,
+                                  a=-.1, b=.2, dw=m.odd_wiener_source,
+                                  dj=m.even_cpoisson_source, seed=5)
+    J._dump_increments = True
+    lx = np.log(np.asarray(J((0., 1.)))[-1])
+    d = J._last_run.dump[0]
+    dJ, dWd = d['dJ'].cpu().numpy()[:, 0], d['dW'].cpu().numpy()[:, 0]
+    assert np.array_equal(dJ[:, :K], dJ[:, K:]) and np.array_equal(dWd[:, :K], -dWd[:, K:])
+    assert 'jump_count' not in J.info
+    # even part of log x: drift + jumps only (the diffusion cancels exactly up to rounding)
+    even = (lx[:K] + lx[K:])/2
+    assert np.allclose(even, -.02 + dJ[:, :K].sum(axis=0), rtol=0, atol=1e-12)
+    # montecarlo antithetic use
+    a = m.montecarlo(lx, use='even')
+    b = m.montecarlo(lx, use='odd')
+    assert a.paths == K and b.paths == K
+    assert np.allclose(a.mean(), even.mean(), rtol=1e-12)
+    assert np.allclose(a.var(), even.var(), rtol=1e-10)
+    odd = (lx[:K] - lx[K:])/2
+    assert np.allclose(b.mean(), odd.mean(), rtol=1e-9, atol=1e-15)
+    assert np.allclose(b.std(), odd.std(), rtol=1e-10)
+    c, e = np.histogram(even, bins=100)
+    assert np.array_equal(a.histogram()[0], c)
+    with pytest.raises(ValueError):
+        m.montecarlo(lx[:-1], use='even')
