@@ -174,6 +174,27 @@ int sdeb_antithetic_fold(const double* x, int64_t n_rows, int64_t half, int64_t 
                          int64_t pitch_out, int64_t sign, double* out, void* stream);
 
 /*
+ * process.cdf / process.chf / process interpolation (infrastructure.py:544-633,
+ * 1125-1209) over the n_paths values of ONE row (one time point, one component).
+ * With interp != 0 the row is the linear interpolation y = w_hi*y_hi + w_lo*y_lo
+ * between two stored rows, w_hi = (t - t_lo)/(t_hi - t_lo), w_lo = (t_hi - t)/(t_hi - t_lo)
+ * evaluated by the caller: scipy.interpolate.interp1d's formula with every
+ * operation separately rounded; with interp == 0 it is y_lo itself.
+ *   sdeb_path_cdf : counts[j] += #{paths : y <= q[j]}            (exact integers)
+ *   sdeb_path_chf : sums[j][0..1] = sum over paths of cos(u[j] y), sin(u[j] y)
+ *   sdeb_path_interp : out[path] = y
+ */
+int64_t sdeb_path_eval_workspace(int64_t nq);
+int sdeb_path_cdf(const double* y_lo, const double* y_hi, double w_lo, double w_hi,
+                  int64_t interp, int64_t n_paths, const double* q, int64_t nq,
+                  int64_t* counts, void* stream);
+int sdeb_path_chf(const double* y_lo, const double* y_hi, double w_lo, double w_hi,
+                  int64_t interp, int64_t n_paths, const double* u, int64_t nq, double* sums,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+int sdeb_path_interp(const double* y_lo, const double* y_hi, double w_lo, double w_hi,
+                     int64_t n_paths, double* out, void* stream);
+
+/*
  * 1-D histogram of x[n] on given edges[nbins+1] with numpy.histogram
  * semantics (half-open bins, last one closed; montecarlo._update_histogram,
  * infrastructure.py:2961-3021).  counts[nbins] and outside[1] are

@@ -69,6 +69,11 @@ def _load():
     lib.sdeb_integrate.argtypes = [C.POINTER(Problem), ptr]
     lib.sdeb_moments.argtypes = [ptr, i64, i64, i64, ptr, ptr, ptr, i64, ptr]
     lib.sdeb_histogram.argtypes = [ptr, i64, ptr, i64, i64, ptr, ptr, ptr]
+    lib.sdeb_path_eval_workspace.restype = i64
+    lib.sdeb_path_eval_workspace.argtypes = [i64]
+    lib.sdeb_path_cdf.argtypes = [ptr, ptr, f64, f64, i64, i64, ptr, i64, ptr, ptr]
+    lib.sdeb_path_chf.argtypes = [ptr, ptr, f64, f64, i64, i64, ptr, i64, ptr, ptr, i64, ptr]
+    lib.sdeb_path_interp.argtypes = [ptr, ptr, f64, f64, i64, ptr, ptr]
     lib.sdeb_antithetic_fold.argtypes = [ptr, i64, i64, i64, i64, i64, ptr, ptr]
     lib.sdeb_draw_wiener.argtypes = [ptr, i64, i64, i64, i64, i64, u64, i64,
                                      f64, ptr, ptr]
@@ -89,7 +94,8 @@ lib = _load()
 
 EXPORTS = ('sdeb_abi_version', 'sdeb_last_error', 'sdeb_device_info',
            'sdeb_plan', 'sdeb_integrate', 'sdeb_moments_workspace',
-           'sdeb_moments', 'sdeb_histogram', 'sdeb_antithetic_fold', 'sdeb_draw_wiener',
+           'sdeb_moments', 'sdeb_histogram', 'sdeb_antithetic_fold', 'sdeb_path_eval_workspace', 'sdeb_path_cdf',
+           'sdeb_path_chf', 'sdeb_path_interp', 'sdeb_draw_wiener',
            'sdeb_draw_cpoisson', 'sdeb_test_normals', 'sdeb_test_philox',
            'sdeb_fp64_peak', 'sdeb_jit_compile', 'sdeb_jit_release')
 

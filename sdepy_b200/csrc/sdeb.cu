@@ -333,6 +333,155 @@ extern "C" int sdeb_antithetic_fold(const double* x, int64_t n_rows, int64_t hal
 }
 
 // ---------------------------------------------------------------------------
+// process.cdf / process.chf / process interpolation over the paths of one row
+// (reference infrastructure.py:544-633, 1125-1209).  The row at time t is
+// y = w_hi*y_hi + w_lo*y_lo, w_hi = (t - t_lo)/(t_hi - t_lo),
+// w_lo = (t_hi - t)/(t_hi - t_lo) (weights evaluated on the host), each
+// product and the sum separately rounded -- the formula of
+// scipy.interpolate.interp1d._call_linear (SciPy 1.18, a third-party
+// dependency of the reference) -- so that cdf counts match the reference
+// exactly.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double row_value(const double* lo, const double* hi, int64_t i,
+                                            double w_lo, double w_hi, double, int interp) {
+    double y = lo[i];
+    if (interp) y = __dadd_rn(__dmul_rn(w_hi, hi[i]), __dmul_rn(w_lo, y));
+    return y;
+}
+
+enum { EVAL_CDF = 0, EVAL_CHF = 1, EVAL_QCHUNK = 8 };
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+path_eval_kernel(const double* lo, const double* hi, double t_lo, double dt_knots, double t,
+                 /* t_lo, dt_knots carry w_lo, w_hi */
+                 int interp, int64_t n_paths, const double* q, int nq,
+                 unsigned long long* counts, double* partials) {
+    __shared__ double s_red[8][2 * EVAL_QCHUNK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q0 = 0; q0 < nq; q0 += EVAL_QCHUNK) {
+        double qv[EVAL_QCHUNK];
+        double a0[EVAL_QCHUNK], a1[EVAL_QCHUNK];
+        unsigned int cnt[EVAL_QCHUNK];
+#pragma unroll
+        for (int j = 0; j < EVAL_QCHUNK; ++j) {
+            qv[j] = (q0 + j < nq) ? q[q0 + j] : 0.0;
+            a0[j] = a1[j] = 0.0; cnt[j] = 0;
+        }
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_paths;
+             i += (int64_t)gridDim.x * blockDim.x) {
+            double y = row_value(lo, hi, i, t_lo, dt_knots, t, interp);
+#pragma unroll
+            for (int j = 0; j < EVAL_QCHUNK; ++j) {
+                if (MODE == EVAL_CDF) {
+                    cnt[j] += (y <= qv[j]) ? 1u : 0u;
+                } else {
+                    double sn, cs;
+                    sincos(qv[j] * y, &sn, &cs);
+                    a0[j] += cs; a1[j] += sn;
+                }
+            }
+        }
+        if (MODE == EVAL_CDF) {
+#pragma unroll
+            for (int j = 0; j < EVAL_QCHUNK; ++j) {
+                unsigned int c = cnt[j];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
+                if (lane == 0 && q0 + j < nq && c) atomicAdd(&counts[q0 + j], (unsigned long long)c);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < EVAL_QCHUNK; ++j) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    a0[j] += __shfl_down_sync(0xffffffffu, a0[j], off);
+                    a1[j] += __shfl_down_sync(0xffffffffu, a1[j], off);
+                }
+                if (lane == 0) { s_red[warp][2*j] = a0[j]; s_red[warp][2*j + 1] = a1[j]; }
+            }
+            __syncthreads();
+            if (threadIdx.x < 2 * EVAL_QCHUNK && q0 + (int)threadIdx.x / 2 < nq) {
+                double acc = 0.0;
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) acc += s_red[w][threadIdx.x];
+                // [block][nq][2]
+                partials[((int64_t)blockIdx.x * nq + q0) * 2 + threadIdx.x] = acc;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void fold_sum_kernel(const double* partials, int64_t n_blocks, int64_t len, double* out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    double acc = 0.0;
+    for (int64_t b = 0; b < n_blocks; ++b) acc += partials[b * len + i];
+    out[i] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+path_interp_kernel(const double* lo, const double* hi, double t_lo /* w_lo */,
+                   double dt_knots /* w_hi */, double t,
+                   int64_t n_paths, double* out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_paths;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = row_value(lo, hi, i, t_lo, dt_knots, t, 1);
+}
+
+static const int kEvalBlocks = 592;
+
+extern "C" int64_t sdeb_path_eval_workspace(int64_t nq) { return (int64_t)kEvalBlocks * nq * 2 * 8; }
+
+extern "C" int sdeb_path_cdf(const double* y_lo, const double* y_hi, double w_lo, double w_hi,
+                             int64_t interp, int64_t n_paths, const double* q,
+                             int64_t nq, int64_t* counts, void* stream_) {
+    if (!y_lo || (interp && !y_hi) || !q || !counts || n_paths < 1 || nq < 1)
+        return fail(SDEB_EINVAL, "sdeb_path_cdf: bad arguments");
+    int64_t need = (n_paths + 255) / 256;
+    int blocks = (int)(need < kEvalBlocks ? need : kEvalBlocks);
+    path_eval_kernel<EVAL_CDF><<<blocks, 256, 0, (cudaStream_t)stream_>>>(
+        y_lo, y_hi, w_lo, w_hi, 0.0, (int)interp, n_paths, q, (int)nq,
+        (unsigned long long*)counts, NULL);
+    CUDA_TRY(cudaGetLastError());
+    return SDEB_OK;
+}
+
+extern "C" int sdeb_path_chf(const double* y_lo, const double* y_hi, double w_lo, double w_hi,
+                             int64_t interp, int64_t n_paths, const double* u,
+                             int64_t nq, double* sums, void* workspace, int64_t workspace_bytes,
+                             void* stream_) {
+    if (!y_lo || (interp && !y_hi) || !u || !sums || n_paths < 1 || nq < 1)
+        return fail(SDEB_EINVAL, "sdeb_path_chf: bad arguments");
+    if (!workspace || workspace_bytes < sdeb_path_eval_workspace(nq))
+        return fail(SDEB_EINVAL, "sdeb_path_chf: workspace too small");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int64_t need = (n_paths + 255) / 256;
+    int blocks = (int)(need < kEvalBlocks ? need : kEvalBlocks);
+    path_eval_kernel<EVAL_CHF><<<blocks, 256, 0, stream>>>(
+        y_lo, y_hi, w_lo, w_hi, 0.0, (int)interp, n_paths, u, (int)nq, NULL,
+        (double*)workspace);
+    CUDA_TRY(cudaGetLastError());
+    int64_t len = nq * 2;
+    fold_sum_kernel<<<(unsigned)((len + 127) / 128), 128, 0, stream>>>(
+        (const double*)workspace, blocks, len, sums);
+    CUDA_TRY(cudaGetLastError());
+    return SDEB_OK;
+}
+
+extern "C" int sdeb_path_interp(const double* y_lo, const double* y_hi, double w_lo, double w_hi,
+                                int64_t n_paths, double* out, void* stream_) {
+    if (!y_lo || !y_hi || !out || n_paths < 1)
+        return fail(SDEB_EINVAL, "sdeb_path_interp: bad arguments");
+    int64_t need = (n_paths + 255) / 256;
+    int blocks = (int)(need < 1184 ? need : 1184);
+    path_interp_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(y_lo, y_hi, w_lo, w_hi, 0.0,
+                                                                  n_paths, out);
+    CUDA_TRY(cudaGetLastError());
+    return SDEB_OK;
+}
+
+// ---------------------------------------------------------------------------
 // histogram with numpy.histogram bin semantics
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

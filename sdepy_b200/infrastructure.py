@@ -265,6 +265,39 @@ class process(np.ndarray):
     def _summary(self, name, **kw):
         return process(t=self.t, x=getattr(self.x, name)(axis=-1, keepdims=True, **kw))
 
+    def _at(self, t):
+        if t is None:
+            return self.t, self.x
+        t = np.asarray(t)
+        return t, self(t)
+
+    def chf(self, t=None, u=None):
+        """Path-average of exp(1j*u*p(t)), shape t.shape + u.shape + vshape
+        (reference infrastructure.py:1125-1167); ``p.chf(u)`` uses the
+        process timeline."""
+        if t is None and u is None:
+            raise TypeError('u argument missing')
+        if u is None:
+            t, u = None, t
+        t, x = self._at(t)
+        u = np.asarray(u)
+        uu = u.reshape((1,)*t.ndim + u.shape + (1,)*(x.ndim - t.ndim))
+        xx = x.reshape(t.shape + (1,)*u.ndim + x.shape[t.ndim:])
+        return np.exp(1j*uu*xx).mean(axis=-1)
+
+    def cdf(self, t=None, x=None):
+        """Fraction of paths with p(t) <= x, shape t.shape + x.shape + vshape
+        (reference infrastructure.py:1169-1209)."""
+        if t is None and x is None:
+            raise TypeError('x argument missing')
+        if x is None:
+            t, x = None, t
+        t, y = self._at(t)
+        x = np.asarray(x)
+        xx = x.reshape((1,)*t.ndim + x.shape + (1,)*(y.ndim - t.ndim))
+        yy = y.reshape(t.shape + (1,)*x.ndim + y.shape[t.ndim:])
+        return (yy <= xx).sum(axis=-1)/self.paths
+
     def psum(self):
         return self._summary('sum')
 
@@ -336,6 +369,107 @@ class device_process:
 
     def _wrap(self, flat):
         return process(t=self.t, x=np.asarray(flat).reshape(self.shape[:-1] + (1,)))
+
+    # ---- interpolation in time, cdf, chf (reference 544-633, 1125-1209) ----
+    def _bracket(self, t):
+        """(i_lo, i_hi, interp) of scipy.interpolate.interp1d(kind='linear',
+        fill_value=(x[0], x[-1])): knots lo = searchsorted(t)-1 clipped; no
+        extrapolation."""
+        tk = self.t
+        if tk.size == 1 or t < tk[0]:
+            return 0, 0, 0
+        if t > tk[-1]:
+            return tk.size - 1, tk.size - 1, 0
+        idx = int(np.clip(np.searchsorted(tk, t), 1, tk.size - 1))
+        return idx - 1, idx, 1
+
+    def _weights(self, lo, hi, t):
+        """Interpolation weights of scipy's interp1d._call_linear."""
+        t_lo, t_hi = self.t[lo], self.t[hi]
+        if lo == hi:
+            return 1., 0.
+        t = np.float64(t)
+        return float((t_hi - t)/(t_hi - t_lo)), float((t - t_lo)/(t_hi - t_lo))
+
+    def _rows2d(self):
+        x = self.x if self.x.is_contiguous() else self.x.contiguous()
+        return x.reshape(x.shape[0], -1, x.shape[-1])       # [N, V, paths]
+
+    def __call__(self, s, ds=None):
+        """Interpolated values ``p(s)`` (or increments ``p(s, ds)``) as a CUDA
+        tensor shaped ``s.shape + vshape + (paths,)``."""
+        s = np.asarray(s, dtype=float)
+        if ds is not None:
+            return self(s + np.asarray(ds, dtype=float)) - self(s)
+        rows = self._rows2d()
+        dev = rows.device
+        out = _cuda.empty((s.size,) + tuple(rows.shape[1:]), dev)
+        with torch.cuda.device(dev):
+            for k, t in enumerate(s.reshape(-1)):
+                lo, hi, interp = self._bracket(float(t))
+                if not interp:
+                    out[k] = rows[lo]
+                    continue
+                w_lo, w_hi = self._weights(lo, hi, t)
+                for v in range(rows.shape[1]):
+                    _lib.check(_lib.lib.sdeb_path_interp(
+                        _cuda.ptr(rows[lo, v]), _cuda.ptr(rows[hi, v]), w_lo, w_hi,
+                        self.paths, _cuda.ptr(out[k, v]), _cuda.stream_ptr(dev)))
+        return out.reshape(s.shape + self.vshape + (self.paths,))
+
+    def _eval(self, t, q, mode):
+        rows = self._rows2d()
+        dev = rows.device
+        q = np.asarray(q, dtype=float)
+        tq = self.t if t is None else np.asarray(t, dtype=float)
+        nq, V = q.size, rows.shape[1]
+        qd = _cuda.to_device(q.reshape(-1), dev)
+        if mode == 'cdf':
+            acc = _cuda.zeros((tq.size, V, nq), dev, torch.int64)
+        else:
+            acc = _cuda.empty((tq.size, V, nq, 2), dev)
+            ws_bytes = _lib.lib.sdeb_path_eval_workspace(nq)
+            ws = _cuda.empty((ws_bytes//8,), dev)
+        with torch.cuda.device(dev):
+            for k, tv in enumerate(tq.reshape(-1)):
+                if t is None:
+                    lo, hi, interp = k, k, 0
+                else:
+                    lo, hi, interp = self._bracket(float(tv))
+                w_lo, w_hi = self._weights(lo, hi, tv)
+                for v in range(V):
+                    args = (_cuda.ptr(rows[lo, v]), _cuda.ptr(rows[hi, v]), w_lo, w_hi,
+                            interp, self.paths, _cuda.ptr(qd), nq)
+                    if mode == 'cdf':
+                        _lib.check(_lib.lib.sdeb_path_cdf(*args, _cuda.ptr(acc[k, v]),
+                                                          _cuda.stream_ptr(dev)))
+                    else:
+                        _lib.check(_lib.lib.sdeb_path_chf(*args, _cuda.ptr(acc[k, v]),
+                                                          _cuda.ptr(ws), ws_bytes,
+                                                          _cuda.stream_ptr(dev)))
+        a = acc.cpu().numpy()
+        if mode == 'cdf':
+            r = a/self.paths                                  # [T, V, nq]
+        else:
+            r = (a[..., 0] + 1j*a[..., 1])/self.paths
+        r = np.moveaxis(r, 1, -1)                             # [T, nq, V]
+        return r.reshape(tq.shape + q.shape + self.vshape)
+
+    def cdf(self, t=None, x=None):
+        """Fraction of paths with ``p(t) <= x`` (reference 1169-1209)."""
+        if t is None and x is None:
+            raise TypeError('x argument missing')
+        if x is None:
+            t, x = None, t
+        return self._eval(t, x, 'cdf')
+
+    def chf(self, t=None, u=None):
+        """Path-average of ``exp(1j*u*p(t))`` (reference 1125-1167)."""
+        if t is None and u is None:
+            raise TypeError('u argument missing')
+        if u is None:
+            t, u = None, t
+        return self._eval(t, u, 'chf')
 
     def psum(self):
         return self._wrap(self._moments()[:, 0])
@@ -984,6 +1118,45 @@ class montecarlo:
 
     def outerr(self):
         return self.outpaths/self.paths
+
+    def _density(self, x, method, bandwidth, kind, cumulative):
+        """Estimate of the sample pdf / cdf from the cumulated density histogram
+        (reference infrastructure.py:3149-3278): Gaussian kernels centred on the
+        bin midpoints (bandwidth x bin width), or interpolation of the
+        histogram."""
+        import scipy.interpolate
+        import scipy.special
+        dens, edges = self.density_histogram()
+        x = np.asarray(x)
+        width = np.diff(edges)
+        mid = (edges[:-1] + edges[1:])/2
+        if method == 'gaussian_kde':
+            z = (x[..., np.newaxis] - mid)/(width*bandwidth)
+            if cumulative:
+                k = width*(scipy.special.erf(z/np.sqrt(2)) + 1)/2
+            else:
+                k = np.exp(-z*z/2)/np.sqrt(2*np.pi)/bandwidth
+            return (k*dens).sum(axis=-1)
+        if method == 'interp':
+            if cumulative:
+                xs = edges
+                ys = np.concatenate(((0.,), (width*dens).cumsum()))
+                fill = (0., 1.)
+            else:
+                xs = np.concatenate((edges[:1], mid, edges[-1:]))
+                ys = np.concatenate(((0.,), dens, (0.,)))
+                fill = 0.
+            return scipy.interpolate.interp1d(
+                xs, ys, kind=kind, assume_sorted=True, bounds_error=False,
+                copy=False, fill_value=fill)(x)
+        raise ValueError("pdf or cdf method should be 'gaussian_kde' or "
+                         "'interp', not {}".format(method))
+
+    def pdf(self, x, method='gaussian_kde', bandwidth=1., kind='linear'):
+        return self._density(x, method, bandwidth, kind, False)
+
+    def cdf(self, x, method='gaussian_kde', bandwidth=1., kind='linear'):
+        return self._density(x, method, bandwidth, kind, True)
 
     m = property(lambda self: self.mean())
     s = property(lambda self: self.std())

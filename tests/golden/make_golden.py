@@ -210,6 +210,19 @@ def main():
         })
     save('stats_lognorm', **arrays)
 
+    # process.cdf / chf / interpolation and montecarlo pdf / cdf on the same sample
+    tq = np.array([-.1, 0., .25, .5, .8, 1., 1.2])
+    xq = np.linspace(.5, 2., 7)
+    uq = np.linspace(-2., 2., 5)
+    xs = np.linspace(.4, 2.2, 11)
+    save('stats_cdf_chf', tq=tq, xq=xq, uq=uq, xs=xs,
+         interp=np.asarray(x(tq)), incr=np.asarray(x(.25, .5)),
+         cdf_tl=x.cdf(xq), cdf_t=x.cdf(tq, xq), chf_tl=x.chf(uq), chf_t=x.chf(tq, uq),
+         mc_pdf=np.stack([mc1[i].pdf(xs) for i in range(2)]),
+         mc_cdf=np.stack([mc1[i].cdf(xs) for i in range(2)]),
+         mc_pdf_i=np.stack([mc1[i].pdf(xs, method='interp') for i in range(2)]),
+         mc_cdf_i=np.stack([mc1[i].cdf(xs, method='interp') for i in range(2)]))
+
     # the reference's own known-answer check: Euler on log x is exact for
     # constant-parameter lognormal on shared increments
     # (sdepy/tests/test_processes.py:681-708)

@@ -76,3 +76,54 @@ def test_histogram_semantics_large_random():
     o.update(x)
     assert np.allclose(a.mean(), o.mean(), rtol=1e-10, atol=1e-15)
     assert np.allclose(a.var(), o.var(), rtol=1e-12)
+
+
+def test_device_process_cdf_chf_interp_match_reference():
+    """process.cdf / chf / interpolation on the HBM-resident container
+    (reference infrastructure.py:544-633, 1125-1209): cdf and interpolated
+    values exactly, chf within 1e-12."""
+    m = sd()
+    g, s = golden('stats_cdf_chf'), golden('stats_lognorm')
+    dp = m.device_process(s['t'], torch.from_numpy(s['x']).cuda())
+    assert np.array_equal(dp(g['tq']).cpu().numpy(), g['interp'])
+    assert np.array_equal(dp(.25, .5).cpu().numpy(), g['incr'])
+    assert np.array_equal(dp.cdf(g['xq']), g['cdf_tl'])
+    assert np.array_equal(dp.cdf(g['tq'], g['xq']), g['cdf_t'])
+    assert dp.chf(g['uq']).shape == g['chf_tl'].shape
+    assert np.allclose(dp.chf(g['uq']), g['chf_tl'], rtol=1e-12, atol=1e-15)
+    assert np.allclose(dp.chf(g['tq'], g['uq']), g['chf_t'], rtol=1e-12, atol=1e-15)
+    with pytest.raises(TypeError):
+        dp.chf()
+
+
+def test_montecarlo_pdf_cdf_match_reference():
+    m = sd()
+    g, s = golden('stats_cdf_chf'), golden('stats_lognorm')
+    a = m.montecarlo(s['x'][-1], bins=25)
+    for i in range(2):
+        assert np.allclose(a[i].pdf(g['xs']), g['mc_pdf'][i], rtol=1e-12)
+        assert np.allclose(a[i].cdf(g['xs']), g['mc_cdf'][i], rtol=1e-12)
+        assert np.allclose(a[i].pdf(g['xs'], method='interp'), g['mc_pdf_i'][i], rtol=1e-12)
+        assert np.allclose(a[i].cdf(g['xs'], method='interp'), g['mc_cdf_i'][i], rtol=1e-12)
+    with pytest.raises(ValueError):
+        a[0].pdf(1., method='nope')
+
+
+def test_cdf_chf_of_a_simulated_process_against_closed_forms():
+    """Wiener process: cdf = Phi(x/sqrt(t)), chf = exp(-u^2 t/2) within Monte
+    Carlo error (the quant tests of the reference, tests/test_quant.py:305-351)."""
+    import scipy.stats
+    m = sd()
+    paths = 400_000
+    x = m.wiener_process(paths=paths, steps=41, seed=6, output='device')(np.linspace(0, 2, 5))
+    xq, uq = np.linspace(-2, 2, 9), np.linspace(-1.5, 1.5, 7)
+    t = np.array([.5, .75, 2.])
+    c = x.cdf(t, xq)
+    want = scipy.stats.norm.cdf(xq[None, :]/np.sqrt(t[:, None]))
+    # .75 is interpolated between knots .5 and 1.: variance is not linear in t for
+    # interpolated values, so compare only the knots exactly on the timeline
+    for k in (0, 2):
+        assert np.abs(c[k] - want[k]).max() < 4*.5/np.sqrt(paths)
+    f = x.chf(t[[0, 2]], uq)
+    wantf = np.exp(-uq[None, :]**2*t[[0, 2], None]/2)
+    assert np.abs(f - wantf).max() < 5/np.sqrt(paths)

@@ -215,3 +215,17 @@ def test_integrate_decorator_infers_equations_and_sources():
         sd.integrate(lambda: 1/0)
     with pytest.raises(TypeError):
         sd.integrate(one.sde, q=3)
+
+
+def test_host_process_cdf_chf_interp_match_reference():
+    from tests.cases import golden
+    g, s = golden('stats_cdf_chf'), golden('stats_lognorm')
+    p = sd.process(s['t'], x=s['x'])
+    assert np.array_equal(p(g['tq']), g['interp'])
+    assert np.array_equal(p(.25, .5), g['incr'])
+    assert np.array_equal(p.cdf(g['xq']), g['cdf_tl'])
+    assert np.array_equal(p.cdf(g['tq'], g['xq']), g['cdf_t'])
+    assert np.allclose(p.chf(g['uq']), g['chf_tl'], rtol=1e-14, atol=1e-16)
+    assert np.allclose(p.chf(g['tq'], g['uq']), g['chf_t'], rtol=1e-14, atol=1e-16)
+    with pytest.raises(TypeError):
+        p.cdf()
