@@ -17,13 +17,14 @@ the single all-reduce of the packed statistics vector).
   e2e   : the same metric through the public API heston_process(...)(timeline)
           with output='stats': host-side lowering, pinned H2D copy of the step /
           parameter tables, kernel, D2H read of the statistics -- every step.
-  roofline : FP64-pipe utilisation.  The kernel has no HBM traffic to speak of
-          and no tensor-core work; its binding resource is the FP64 pipe, so
-          bound="fp64", achieved = executed FP64-pipe warp-instructions/s
-          (N64 per path-step, counted from the SASS of the per-step path and
-          cross-checked by ncu) against the DFMA rate measured
-          live by sdeb_fp64_peak(); both expressed as TFLOP/s with 2 flop per
-          FP64-pipe lane-instruction.
+  roofline : the kernel has no HBM traffic to speak of and no tensor-core
+          work; its bound is the FP64 pipe (bound="fp64").  achieved =
+          ALGORITHMIC work per SURVEY.md 8(d) (100 FP64-pipe instructions per
+          Heston path-step at libdevice transcendental costs) x path-steps/s,
+          peak = DFMA rate measured live by sdeb_fp64_peak(); both in TFLOP/s
+          (2 flop per FP64 lane-instruction).  roofline.executed reports the
+          pipe utilisation of what the kernel really issues (53 FP64
+          instructions per path-step; = ncu sm__pipe_fp64_cycles_active).
   cpu_baseline : the NumPy oracle port of the reference's Heston path, one
           core, on a bounded sample, same box, same run.
 
@@ -49,9 +50,14 @@ HESTON = dict(x0=100., mu=.03, sigma=1., y0=.04, theta=.04, k=2., xi=.3)
 RHO = -.7
 N_STEPS = 252
 STRIKE, RATE = 100., .03
-# FP64-pipe warp-instructions executed per Heston path-step on the Philox /
-# no-store path of integrate_kernel<HestonSDE<1,false>> (DFMA+DMUL+DADD+DSETP
-# in the SASS between the step-loop head and the store check)
+# ALGORITHMIC work per Heston path-step, SURVEY.md section 8(d): 34 fp64 flop
+# counting each sqrt/log/sin/cos as one = ~100 FP64-pipe instructions with
+# libdevice transcendental costs.  This is the per-unit figure of the roofline.
+ALGO_FP64_INSTR_PER_PATH_STEP = 100
+# FP64-pipe warp-instructions this kernel actually EXECUTES per path-step
+# (hand-rolled log / sqrt / sincos): DFMA+DMUL+DADD+DSETP on the Philox /
+# no-store path of integrate_lean_kernel<HestonSDE<1,false>>, SASS count,
+# confirmed by ncu sm__inst_executed_pipe_fp64.sum / path-steps = 53.5
 N64_PER_PATH_STEP = 53
 
 
@@ -287,7 +293,8 @@ def run_ours(a):
         _lib.check(_lib.lib.sdeb_fp64_peak(200_000, ctypes.byref(peak), _cuda.stream_ptr(dev)))
         peak_tf = peak.value*2/1e12
         per_gpu = value/world
-        achieved_tf = per_gpu*N64_PER_PATH_STEP*2/1e12
+        achieved_tf = per_gpu*ALGO_FP64_INSTR_PER_PATH_STEP*2/1e12
+        executed_tf = per_gpu*N64_PER_PATH_STEP*2/1e12
         n = paths
         pay_mean = sums[-1, 0, 6]/n
         pay_se = float(np.sqrt(max(sums[-1, 0, 7]/n - pay_mean**2, 0)/(n - 1)))
@@ -304,11 +311,17 @@ def run_ours(a):
             'roofline': {
                 'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf,
                 'unit': 'TFLOP/s', 'frac': achieved_tf/peak_tf, 'traffic': None,
-                'note': 'FP64-pipe utilisation: %d FP64-pipe instr per path-step '
-                        '(SASS count) x path-steps/s x 2 flop, against the DFMA '
-                        'rate measured live by sdeb_fp64_peak (per GPU); '
-                        'MEASURED_PEAKS.json holds no FP64 figure'
-                        % N64_PER_PATH_STEP},
+                'executed': {'fp64_instr_per_path_step': N64_PER_PATH_STEP,
+                             'achieved': executed_tf, 'frac': executed_tf/peak_tf},
+                'note': 'per GPU. achieved = ALGORITHMIC work (SURVEY 8d: %d FP64-pipe '
+                        'instr per Heston path-step with libdevice transcendental '
+                        'costs) x path-steps/s x 2 flop; peak = DFMA rate measured '
+                        'live by sdeb_fp64_peak (MEASURED_PEAKS.json holds no FP64 '
+                        'figure). "executed" is the FP64-pipe utilisation of the '
+                        'instructions this kernel really issues (%d per path-step: '
+                        'its log/sqrt/sincos are hand-rolled), = ncu '
+                        'sm__pipe_fp64_cycles_active'
+                        % (ALGO_FP64_INSTR_PER_PATH_STEP, N64_PER_PATH_STEP)},
             'check': {'call_price_last_step': pay_mean, 'stderr': pay_se,
                       'closed_form': 9.2425, 'e2e_price': price},
             'wall_s_timed_region': wall,

@@ -158,18 +158,26 @@ extern "C" int sdeb_plan(const sdeb_problem* p, sdeb_plan_t* plan) {
     return plan_impl(p, plan, mi, false);
 }
 
-// fold per-block statistics partials in block order (deterministic)
+// fold per-block statistics partials (deterministic: fixed lane assignment and
+// shuffle tree).  One warp per output element; lane l takes blocks l, l+32, ...
 __global__ void fold_partials_kernel(const double* partials, int64_t n_blocks, int64_t len,
                                      double* stats) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (i >= len) return;
-    int k = (int)(i % NSTAT);
-    double acc = partials[i];
-    for (int64_t b = 1; b < n_blocks; ++b) {
+    const int k = (int)(i % NSTAT);
+    double acc = (k == 4) ? __longlong_as_double(0x7FF0000000000000LL)
+               : (k == 5) ? __longlong_as_double(0xFFF0000000000000LL) : 0.0;
+    for (int64_t b = lane; b < n_blocks; b += 32) {
         double o = partials[b * len + i];
         acc = (k == 4) ? fmin(acc, o) : (k == 5) ? fmax(acc, o) : acc + o;
     }
-    stats[i] = acc;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double o = __shfl_down_sync(0xffffffffu, acc, off);
+        acc = (k == 4) ? fmin(acc, o) : (k == 5) ? fmax(acc, o) : acc + o;
+    }
+    if (lane == 0) stats[i] = acc;
 }
 
 extern "C" int sdeb_integrate(const sdeb_problem* p, void* stream_) {
@@ -222,7 +230,7 @@ extern "C" int sdeb_integrate(const sdeb_problem* p, void* stream_) {
                               (size_t)plan.smem_bytes, stream));
     if (p->stats) {
         int64_t len = p->n_rows * p->n_groups * mi.nx * NSTAT;
-        fold_partials_kernel<<<(unsigned)((len + 127) / 128), 128, 0, stream>>>(
+        fold_partials_kernel<<<(unsigned)((len * 32 + 127) / 128), 128, 0, stream>>>(
             (const double*)p->workspace, plan.blocks, len, p->stats);
         CUDA_TRY(cudaGetLastError());
     }
@@ -297,7 +305,7 @@ extern "C" int sdeb_moments(const double* x, int64_t n_rows, int64_t n_paths, in
         x, n_paths, pitch, centre, (double*)workspace);
     CUDA_TRY(cudaGetLastError());
     int64_t len = n_rows * NSTAT;
-    fold_partials_kernel<<<(unsigned)((len + 127) / 128), 128, 0, stream>>>(
+    fold_partials_kernel<<<(unsigned)((len * 32 + 127) / 128), 128, 0, stream>>>(
         (const double*)workspace, blocks, len, stats);
     CUDA_TRY(cudaGetLastError());
     return SDEB_OK;

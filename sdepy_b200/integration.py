@@ -589,12 +589,20 @@ class SDE(_jit._traced):
         segs = _engine.segments_of(tt, grid, self.i0)
         spec, lead = self._spec()
         replay = self._noise_plan(segs)
-        w0 = self._initial_state(tt[self.i0])
-        npaths0 = w0.shape[-1]
-        w0l = w0.reshape((spec.groups, spec.nw, npaths0))
-        w0_arg = w0l if npaths0 > 1 else w0l[..., 0]
-        records = [self._records(spec, seg, lead, replay is not None)
-                   for seg in segs]
+        # the lowered tables depend only on the grid and on the parameters:
+        # repeated calls (Monte Carlo batches) reuse them
+        key = self._lowering_key(tt, grid, replay is not None)
+        cached = getattr(self, '_lowered', None)
+        if cached is not None and cached[0] == key:
+            w0l, w0_arg, records = cached[1]
+        else:
+            w0 = self._initial_state(tt[self.i0])
+            npaths0 = w0.shape[-1]
+            w0l = w0.reshape((spec.groups, spec.nw, npaths0))
+            w0_arg = w0l if npaths0 > 1 else w0l[..., 0]
+            records = [self._records(spec, seg, lead, replay is not None)
+                       for seg in segs]
+            self._lowered = (key, (w0l, w0_arg, records))
         if replay is not None:
             replay = [{k: (v.reshape((seg.n_steps, -1, self.paths)))
                        for k, v in tab.items()} for tab, seg in zip(replay, segs)]
@@ -633,6 +641,21 @@ class SDE(_jit._traced):
         if self.output == 'process':
             xx = xx.cpu().numpy()
         return xx
+
+    def _lowering_key(self, tt, grid, replay):
+        def ident(z):
+            if isinstance(z, np.ndarray):
+                return (z.shape, z.tobytes()) if z.size <= 4096 else id(z)
+            if isinstance(z, (int, float, complex, str, type(None))):
+                return z
+            return id(z)
+        srcs = []
+        for k in ('dw', 'dj'):
+            src = self.sources.get(k)
+            srcs.append((id(src), ident(getattr(src, 'corr', None)), ident(getattr(src, 'lam', None)),
+                         id(getattr(src, 'y', None))))
+        return (tt.tobytes(), grid.tobytes(), self.i0, replay, self.method,
+                tuple((k, ident(v)) for k, v in sorted(self._args.items())), tuple(srcs))
 
     def _device_info(self, res, tt, segs, replay):
         pass
