@@ -84,13 +84,16 @@ typedef struct sdeb_problem {
     int64_t row0;             /* row receiving the initial state, or -1         */
     int64_t n_psteps;         /* 1: time-invariant params; n_steps: per-step    */
     int64_t w0_per_path;      /* w0 carries a trailing path axis                */
-    int64_t reserved0;        /* must be 0                                      */
+    int64_t params_per_path;  /* records carry a trailing path axis:
+                                 params[n_psteps][n_groups][npt][pitch] (parameters that
+                                 vary along the paths axis, e.g. process-valued ones) */
     uint64_t seed;            /* Philox key                                     */
     const double* steps;      /* [n_steps][2]: dt = t[n+1]-t[n] (integration.py:714),
                                  sqrt|dt| (infrastructure.py:1558-1559)         */
     const int32_t* store_row; /* [n_steps]: row storing the state after step n
                                  (integration.py:386 exact-equality store), -1 = none */
-    const double* params;     /* [n_psteps][n_groups][npt] records, see sdeb_plan */
+    const double* params;     /* [n_psteps][n_groups][npt] records (+[pitch] when
+                                 params_per_path), see sdeb_plan                   */
     const double* params_host;/* optional HOST copy of the same records: a single
                                  time-invariant record (n_psteps == n_groups == 1)
                                  is then passed in the kernel-argument constant

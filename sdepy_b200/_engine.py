@@ -76,6 +76,26 @@ def chol_entries(L, ndw):
     return np.asarray(L, dtype=float)[np.tril_indices(ndw)]
 
 
+def assemble_records(blocks, spec):
+    """blocks: per record step, (model block [G, npc(, paths)], chol entries
+    [nchol]).  Returns [n, G, npt] or, if any block is path-dependent,
+    [n, G, npt, paths]."""
+    pp = [b for b, _ in blocks if b.ndim == 3]
+    n = len(blocks)
+    if not pp:
+        rec = np.zeros((n, spec.groups, spec.npt))
+        for i, (b, L) in enumerate(blocks):
+            rec[i, :, :spec.npc] = b
+            rec[i, :, spec.npc:] = L
+        return rec
+    paths = pp[0].shape[-1]
+    rec = np.zeros((n, spec.groups, spec.npt, paths))
+    for i, (b, L) in enumerate(blocks):
+        rec[i, :, :spec.npc] = b if b.ndim == 3 else b[..., None]
+        rec[i, :, spec.npc:] = np.asarray(L)[None, :, None]
+    return rec
+
+
 class run_result:
     pass
 
@@ -116,7 +136,10 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
     for k, seg in enumerate(segs):
         n = seg.n_steps
         rec = np.ascontiguousarray(records[k], dtype=float)
-        assert rec.shape[1:] == (spec.groups, spec.npt), (rec.shape, spec.groups, spec.npt)
+        assert rec.shape[1:3] == (spec.groups, spec.npt), (rec.shape, spec.groups, spec.npt)
+        per_path = rec.ndim == 4
+        if per_path and rec.shape[3] != paths:
+            raise ValueError('path-dependent parameters need a paths axis of {}'.format(paths))
         p = _lib.Problem()
         p.abi_version = _lib.ABI_VERSION
         p.model, p.ncomp, p.jit_handle = spec.model, spec.ncomp, spec.jit_handle
@@ -134,7 +157,9 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
         keep += [steps_d, rows_d, rec_d]
         p.steps, p.store_row = steps_d.data_ptr(), rows_d.data_ptr()
         p.params, p.w0 = rec_d.data_ptr(), w0_d.data_ptr()
-        p.params_host = rec.ctypes.data          # rec stays alive in `keep`
+        p.params_per_path = int(per_path)
+        if not per_path:
+            p.params_host = rec.ctypes.data      # rec stays alive in `keep`
         keep.append(rec)
         if replay is not None:
             tabs = replay[k]

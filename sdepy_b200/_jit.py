@@ -26,7 +26,7 @@ import os
 import numpy as np
 
 from . import _engine, _lib
-from .infrastructure import lane_values, wiener_source, cpoisson_source
+from .infrastructure import lane_values, stack_lane_columns, wiener_source, cpoisson_source
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -450,36 +450,32 @@ class _traced:
         corr_t = not replay and isinstance(dw, wiener_source) and callable(dw.corr)
         jumps_t = spec.jumps and not replay
         n = seg.n_steps if (tdep or corr_t or jumps_t) and seg.n_steps else 1
-        rec = np.zeros((n, spec.groups, spec.npt))
-        per = jit['nleaf'] + (6 if spec.jumps else 0)
         ncomp = self._rec_comps
+        blocks = []
         for i in range(n):
             s = seg.s[i] if seg.n_steps else 0.
             ds = seg.ds[i] if seg.n_steps else 0.
             leaves = vals[0] if (i == 0 or not tdep) else self._leaf_values(float(s))
-            cols = [lane_values(v, lanes, 'SDE parameter').reshape(spec.groups, ncomp)
-                    for v in leaves]
+            cols = [lane_values(v, lanes, 'SDE parameter', paths=self.paths) for v in leaves]
             if spec.jumps:
-                zero = np.zeros((spec.groups, ncomp))
+                zero = np.zeros(spec.groups*ncomp)
                 if replay:
                     cols += [zero]*6
                 else:
                     mid = s + ds/2
-                    lam = lane_values(dj.dn.lam_at(mid), lanes, 'lam').reshape(spec.groups, ncomp)
+                    lam = lane_values(dj.dn.lam_at(mid), lanes, 'lam', paths=self.paths)
                     lamdt = np.abs(ds)*lam
                     kind, a, b, pa = dj.y.at(mid)
                     cols += [lamdt, np.exp(-lamdt), zero + kind] + [
-                        lane_values(z, lanes, 'jump law parameter').reshape(spec.groups, ncomp)
+                        lane_values(z, lanes, 'jump law parameter', paths=self.paths)
                         for z in (a, b, pa)]
-            if cols:
-                block = np.stack(cols, axis=-1)              # [G, ncomp, per]
-                rec[i, :, :spec.npc] = block.reshape(spec.groups, ncomp*per)
-            if spec.nchol:
-                L = None
-                if not replay and isinstance(dw, wiener_source):
-                    L = dw.chol_at(s + ds/2)
-                rec[i, :, spec.npc:] = _engine.chol_entries(L, spec.ndw)
-        return rec
+            block = (stack_lane_columns(cols, spec.groups, ncomp) if cols
+                     else np.zeros((spec.groups, 0)))
+            L = None
+            if spec.nchol and not replay and isinstance(dw, wiener_source):
+                L = dw.chol_at(s + ds/2)
+            blocks.append((block, _engine.chol_entries(L, spec.ndw)))
+        return _engine.assemble_records(blocks, spec)
 
     # ---- code generation ----------------------------------------------------
     def _codegen_single(self, tr, roots, mil):

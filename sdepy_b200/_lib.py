@@ -28,7 +28,7 @@ class Problem(C.Structure):
         ('jit_handle', i64), ('noise', i64), ('n_paths', i64),
         ('path_offset', i64), ('pitch', i64), ('n_steps', i64),
         ('n_groups', i64), ('n_rows', i64), ('row0', i64),
-        ('n_psteps', i64), ('w0_per_path', i64), ('reserved0', i64),
+        ('n_psteps', i64), ('w0_per_path', i64), ('params_per_path', i64),
         ('seed', u64),
         ('steps', ptr), ('store_row', ptr), ('params', ptr),
         ('params_host', ptr), ('w0', ptr),

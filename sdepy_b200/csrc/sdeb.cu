@@ -98,7 +98,7 @@ static int64_t smem_bytes(const ModelInfo& mi, const sdeb_problem* p, bool stats
 static bool use_lean(const sdeb_problem* p, const ModelInfo& mi) {
     return mi.fn_lean && p->noise == SDEB_NOISE_PHILOX && p->params_host &&
            p->n_psteps == 1 && p->n_groups == 1 && !p->dW_dump && !p->dJ_dump && !p->dN_dump &&
-           !p->anti_dw_half && !p->anti_dj_half;
+           !p->anti_dw_half && !p->anti_dj_half && !p->params_per_path;
 }
 
 static int plan_impl(const sdeb_problem* p, sdeb_plan_t* plan, ModelInfo& mi, bool need_device) {
@@ -214,7 +214,7 @@ extern "C" int sdeb_integrate(const sdeb_problem* p, void* stream_) {
     a.n_paths = p->n_paths; a.path_offset = p->path_offset; a.pitch = p->pitch;
     a.n_steps = (int)p->n_steps; a.n_groups = (int)p->n_groups; a.n_rows = (int)p->n_rows;
     a.row0 = (int)p->row0; a.n_psteps = (int)p->n_psteps; a.w0_per_path = (int)p->w0_per_path;
-    a.noise = (int)p->noise;
+    a.noise = (int)p->noise; a.params_pp = (int)p->params_per_path;
     a.payoff_kind = (int)p->payoff_kind; a.payoff_strike = p->payoff_strike;
     a.payoff_scale = p->payoff_scale;
     a.seed = p->seed;

@@ -750,19 +750,40 @@ class cpoisson_source(source):
         return dj
 
 
-def lane_values(z, lead_shape, what='parameter'):
-    """Broadcast a (vshape-wise) parameter value to one scalar per lane.
-    Parameters follow the reference's convention of broadcasting against
-    ``vshape + (paths,)``; values that really vary along the paths axis are not
-    supported on the device path."""
+def lane_values(z, lead_shape, what='parameter', paths=None):
+    """Broadcast a parameter value against ``vshape + (paths,)`` (the
+    reference's convention) and return one scalar per lane, shape ``[lanes]``
+    -- or, when the value really varies along the paths axis and ``paths`` is
+    given, one row per lane, shape ``[lanes, paths]``."""
     z = np.asarray(z, dtype=float)
+    lead = tuple(lead_shape)
     try:
-        return np.broadcast_to(z, tuple(lead_shape) + (1,)).reshape(-1).copy()
+        return np.broadcast_to(z, lead + (1,)).reshape(-1).copy()
     except ValueError:
-        raise NotImplementedError(
-            '{} of shape {} does not broadcast to vshape + (1,) = {}: '
-            'path-dependent parameters are not supported by the CUDA path'
-            .format(what, z.shape, tuple(lead_shape) + (1,)))
+        pass
+    if paths is not None:
+        try:
+            return np.broadcast_to(z, lead + (paths,)).reshape(-1, paths).copy()
+        except ValueError:
+            pass
+    raise ValueError(
+        '{} of shape {} does not broadcast to vshape + (paths,) = {}'
+        .format(what, z.shape, lead + (paths if paths is not None else 1,)))
+
+
+def stack_lane_columns(cols, groups, ncomp):
+    """cols: per-lane values, each ``[lanes]`` or ``[lanes, paths]``.  Returns the
+    record block ``[groups, ncomp*len(cols)]`` or, if any column is
+    path-dependent, ``[groups, ncomp*len(cols), paths]`` (component-major)."""
+    pp = [c for c in cols if c.ndim == 2]
+    if not pp:
+        block = np.stack([c.reshape(groups, ncomp) for c in cols], axis=-1)
+        return block.reshape(groups, ncomp*len(cols))
+    paths = pp[0].shape[-1]
+    full = [np.broadcast_to(c[:, None] if c.ndim == 1 else c, (groups*ncomp, paths))
+            .reshape(groups, ncomp, paths) for c in cols]
+    block = np.stack(full, axis=2)                       # [G, ncomp, per, paths]
+    return block.reshape(groups, ncomp*len(cols), paths)
 
 
 def _draw_cpoisson(src, dn_src, law, t, dt, want_dj):

@@ -21,7 +21,7 @@ from . import _cuda, _engine, _jit, _lib
 from .infrastructure import (
     process, device_process, wiener_source, poisson_source, cpoisson_source,
     odd_wiener_source, even_cpoisson_source,
-    replay_source, norm_rv, double_exp_rv, lane_values, _law,
+    replay_source, norm_rv, double_exp_rv, lane_values, stack_lane_columns, _law,
     _shape_setup, _const_param_setup, _variable_param_setup, _source_setup,
     _get_default_rng, _signature, _empty)
 
@@ -842,11 +842,11 @@ class _preset_SDE(SDE):
         n = seg.n_steps if (tdep or corr_t or jumps_t) else 1
         n = max(n, 1) if seg.n_steps else 1
         ncomp = spec.ncomp
-        rec = np.zeros((n, spec.groups, spec.npt))
-        # parameters broadcast against the working shape (+ a paths axis of 1);
+        # parameters broadcast against the working shape (+ the paths axis);
         # its prod(lead) x ncomp elements map to [group, component]
         full = self._param_target()
         assert int(np.prod(full, dtype=int)) == spec.groups*ncomp
+        blocks = []
         for i in range(n):
             s = seg.s[i] if seg.n_steps else 0.
             ds = seg.ds[i] if seg.n_steps else 0.
@@ -854,27 +854,22 @@ class _preset_SDE(SDE):
             cols = [self._lane_matrix(c, full) for c in self._coeffs(p)]
             if spec.jumps:
                 cols += self._jump_cols(dj, s, ds, full, replay)
-            block = np.stack(cols, axis=-1)                 # [G, ncomp, per]
-            rec[i, :, :spec.npc] = block.reshape(spec.groups, spec.npc)
-            if spec.nchol:
-                L = None
-                if not replay and isinstance(dw, wiener_source):
-                    L = dw.chol_at(s + ds/2)               # midpoint, 1540
-                rec[i, :, spec.npc:] = _engine.chol_entries(L, spec.ndw)
-        return rec
+            block = stack_lane_columns(cols, spec.groups, ncomp)   # [G, npc(, paths)]
+            L = None
+            if spec.nchol and not replay and isinstance(dw, wiener_source):
+                L = dw.chol_at(s + ds/2)                           # midpoint, 1540
+            blocks.append((block, _engine.chol_entries(L, spec.ndw)))
+        return _engine.assemble_records(blocks, spec)
 
     def _param_target(self):
         return self.wshape
 
     def _lane_matrix(self, value, full):
-        """Broadcast a coefficient against wshape (+ trailing paths axis of
-        size 1) and reshape to [groups, ncomp]."""
-        v = lane_values(value, full, 'SDE parameter')
-        return v.reshape(-1, self._lanes()[1])
+        """Per-lane values of a coefficient: [lanes] or [lanes, paths]."""
+        return lane_values(value, full, 'SDE parameter', paths=self.paths)
 
     def _jump_cols(self, dj, s, ds, full, replay):
-        ncomp = self._lanes()[1]
-        zero = np.zeros((int(np.prod(full, dtype=int))//ncomp, ncomp))
+        zero = np.zeros(int(np.prod(full, dtype=int)))
         if replay:
             return [zero]*6
         mid = s + ds/2

@@ -177,3 +177,45 @@ def test_antithetic_sources_and_montecarlo_use():
     assert np.array_equal(a.histogram()[0], c)
     with pytest.raises(ValueError):
         m.montecarlo(lx[:-1], use='even')
+
+
+def test_path_dependent_and_process_valued_parameters():
+    """Parameters shaped (..., paths) and multi-path `process` instances as
+    parameters (reference doc/quickguide.rst:127-137, 404-412): replay parity
+    with the oracle, which broadcasts them natively."""
+    m = sd()
+    rng = np.random.default_rng(4)
+    paths, n = 333, 20
+    grid = np.linspace(0., 1., n + 1)
+    dW = rng.standard_normal((n, paths))*np.sqrt(1/n)
+    mu, sigma = rng.normal(.05, .02, paths), .1 + .2*rng.random(paths)
+    out, _ = orc.euler_replay('lognorm', dict(mu=mu, sigma=sigma), 1., grid, [0, 7, n], dW)
+    x = m.lognorm_process(paths=paths, steps=grid, x0=1., mu=mu, sigma=sigma,
+                          dw=m.replay_source(dW))(grid[[0, 7, n]])
+    assert np.abs(np.asarray(x)/out - 1).max() <= 4*np.finfo(float).eps
+    # Heston with a path-dependent vol-of-vol, y bit-exact
+    dW2 = rng.standard_normal((n, 2, paths))*np.sqrt(1/n)
+    xi = .2 + .6*rng.random(paths)
+    par = dict(mu=.03, sigma=1., theta=.04, k=2., xi=xi)
+    (ox, oy), oi = orc.euler_replay('heston', par, 100., grid, [0, n], dW2, y0=.04, full=True)
+    P = m.full_heston_process(paths=paths, steps=grid, x0=100., y0=.04,
+                              dw=m.replay_source(dW2), **par)
+    hx, hy = P((0., 1.))
+    assert np.array_equal(np.asarray(hy), oy)
+    assert np.array_equal(P.info['negative_y_count'], oi['negative_y_count'])
+    # time- and path-dependent: a multi-path process as the OU mean level
+    tk = np.linspace(0., 1., 5)
+    level = m.process(tk, x=rng.normal(.5, .1, (5, paths)).cumsum(axis=0))
+    par = dict(theta=level, k=1.5, sigma=.3)
+    out, _ = orc.euler_replay('ornstein_uhlenbeck', par, .2, grid, [0, n], dW)
+    x = m.ornstein_uhlenbeck_process(paths=paths, steps=grid, x0=.2,
+                                     dw=m.replay_source(dW), **par)((0., 1.))
+    assert np.array_equal(np.asarray(x), out)
+
+    # traced SDE with a path-dependent parameter, philox mode: per-path drift shows up
+    @m.integrate
+    def f(t, x, a=0., s=1.):
+        return {'dt': a, 'dw': s}
+    a = np.where(np.arange(20_000) % 2, 1., -1.)
+    y = np.asarray(f(paths=20_000, steps=11, x0=0., a=a, s=.1, seed=2)((0., 1.)))[-1]
+    assert abs(y[1::2].mean() - 1.) < .01 and abs(y[0::2].mean() + 1.) < .01

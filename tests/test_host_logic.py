@@ -111,11 +111,16 @@ def test_vshape_lanes():
     assert H._lanes() == ((4,), 2) and H.wshape == (4, 2) and H.xshape == (4,)
     F = sd.full_heston_process(paths=5, vshape=(2,))
     assert F.wshape == (4,) and F._lanes() == ((), 2)
-    with pytest.raises(NotImplementedError):
-        B = sd.lognorm_process(paths=5, mu=np.arange(5.))
-        spec, lead = B._spec()
-        seg, = _engine.segments_of(np.array([0., 1.]), np.array([0., 1.]), 0)
-        B._records(spec, seg, lead, False)
+    # a parameter with a real paths axis gives path-dependent records
+    B = sd.lognorm_process(paths=5, mu=np.arange(5.), sigma=.5)
+    spec, lead = B._spec()
+    seg, = _engine.segments_of(np.array([0., 1.]), np.array([0., 1.]), 0)
+    rec = B._records(spec, seg, lead, False)
+    assert rec.shape == (1, 1, 2, 5)
+    assert np.array_equal(rec[0, 0, 0], np.arange(5.) - .5*.5/2) and (rec[0, 0, 1] == .5).all()
+    with pytest.raises(ValueError):
+        C2 = sd.lognorm_process(paths=5, mu=np.arange(4.))
+        C2._records(*((C2._spec()[0], seg, C2._spec()[1], False)))
 
 
 def test_construction_errors():
