@@ -26,7 +26,7 @@ import os
 import numpy as np
 
 from . import _engine, _lib
-from .infrastructure import lane_values, stack_lane_columns, wiener_source, cpoisson_source
+from .infrastructure import lane_values, stack_lane_columns, wiener_source
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -439,7 +439,7 @@ class _traced:
 
     def _records(self, spec, seg, lead, replay):
         jit = self._jit
-        dw, dj = self.sources.get('dw'), self.sources.get('dj')
+        dw, dj = self.sources.get('dw'), self._jump_source()
         lanes = self._param_target()
         # is anything time-dependent?  (callable parameters, explicit use of t)
         probe = [float(seg.s[0]), float(seg.s[-1])] if seg.n_steps else [0.]
@@ -463,9 +463,14 @@ class _traced:
                     cols += [zero]*6
                 else:
                     mid = s + ds/2
-                    lam = lane_values(dj.dn.lam_at(mid), lanes, 'lam', paths=self.paths)
+                    if 'dn' in self.sources:     # plain Poisson: unit jump sizes
+                        lam_src = dj
+                        kind, a, b, pa = _lib.LAW_UNIFORM, 1., 1., 0.
+                    else:
+                        lam_src = dj.dn
+                        kind, a, b, pa = dj.y.at(mid)
+                    lam = lane_values(lam_src.lam_at(mid), lanes, 'lam', paths=self.paths)
                     lamdt = np.abs(ds)*lam
-                    kind, a, b, pa = dj.y.at(mid)
                     cols += [lamdt, np.exp(-lamdt), zero + kind] + [
                         lane_values(z, lanes, 'jump law parameter', paths=self.paths)
                         for z in (a, b, pa)]
@@ -481,17 +486,17 @@ class _traced:
     def _codegen_single(self, tr, roots, mil):
         lead, m = self._lanes()
         ids = [k for k, _ in roots[0]]
-        unknown = set(ids) - {'dt', 'dw', 'dj'}
+        unknown = set(ids) - {'dt', 'dw', 'dj', 'dn'}
         if unknown:
             raise NotImplementedError('differentials {} have no device '
                                       'implementation'.format(unknown))
-        jumps = 'dj' in self.sources
+        jumps = self._jump_source() is not None
         nleaf = len(tr.leaves)
         per = nleaf + (6 if jumps else 0)
         em = emitter(lambda k: 'p[%d*c + %d]' % (per, k), lambda i: 'x[c]')
         terms = []
         for k, nd in roots[0]:
-            dz = {'dt': 'ds', 'dw': 'dw[c]', 'dj': 'dj[c]'}[k]
+            dz = {'dt': 'ds', 'dw': 'dw[c]', 'dj': 'dj[c]', 'dn': 'dj[c]'}[k]
             terms.append('xmul(%s, %s)' % (em.ref(nd), dz))
         inc = terms[0]
         for tm in terms[1:]:

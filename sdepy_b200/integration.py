@@ -17,11 +17,11 @@ default --, 'device' HBM-resident container, 'stats' fused statistics only),
 import numpy as np
 import torch
 
-from . import _cuda, _engine, _jit, _lib
+from . import _engine, _jit, _lib
 from .infrastructure import (
     process, device_process, wiener_source, poisson_source, cpoisson_source,
-    odd_wiener_source, even_cpoisson_source,
-    replay_source, norm_rv, double_exp_rv, lane_values, stack_lane_columns, _law,
+    odd_wiener_source, even_cpoisson_source, even_poisson_source,
+    replay_source, norm_rv, double_exp_rv, lane_values, stack_lane_columns,
     _shape_setup, _const_param_setup, _variable_param_setup, _source_setup,
     _get_default_rng, _signature, _empty)
 
@@ -511,14 +511,15 @@ class SDE(_jit._traced):
         1233) -- and fed to the kernel in replay mode.  That covers replay
         tables, the reference's own source objects and ``process`` instances.
         """
-        dw, dj = self.sources.get('dw'), self.sources.get('dj')
-        unknown = set(self.sources) - {'dt', 'dw', 'dj'}
+        dw, dj = self.sources.get('dw'), self._jump_source()
+        unknown = set(self.sources) - {'dt', 'dw', 'dj', 'dn'}
         if unknown:
             raise NotImplementedError(
                 'sources {} have no device implementation'.format(unknown))
         philox_ok = (dw is None or type(dw) in (wiener_source, odd_wiener_source)) and (
-            dj is None or (type(dj) in (cpoisson_source, even_cpoisson_source)
-                           and dj.device_ready()))
+            dj is None or
+            (type(dj) in (cpoisson_source, even_cpoisson_source) and dj.device_ready()) or
+            type(dj) in (poisson_source, even_poisson_source))
         if philox_ok:
             return None
         tables = []
@@ -545,7 +546,7 @@ class SDE(_jit._traced):
             rows = {'dW': [], 'dJ': [], 'dN': []}
             for s, ds in zip(seg.s, seg.ds):
                 for id in self._ordered_source_ids:
-                    if id == 'dj':
+                    if id in ('dj', 'dn'):
                         z = dj(s, ds)
                         rows['dJ'].append(self._as_lane_table(z))
                         if hasattr(dj, 'dn_value'):
@@ -571,8 +572,17 @@ class SDE(_jit._traced):
             z = z.astype(np.int64)
         return np.broadcast_to(z, shape)
 
+    def _jump_source(self):
+        """The source feeding the kernel's jump slot: the compound Poisson
+        source 'dj', or a plain Poisson source 'dn' (unit jump sizes)."""
+        if 'dj' in self.sources and 'dn' in self.sources:
+            raise NotImplementedError(
+                "an SDE with both 'dn' and 'dj' differentials has no device "
+                'implementation')
+        return self.sources.get('dj', self.sources.get('dn'))
+
     def _philox_key(self):
-        for id in ('dw', 'dj'):
+        for id in ('dw', 'dj', 'dn'):
             src = self.sources.get(id)
             if hasattr(src, 'next_key'):
                 return src.next_key()
@@ -612,7 +622,7 @@ class SDE(_jit._traced):
         anti = {}
         if replay is None:
             for key, src in (('anti_dw_half', self.sources.get('dw')),
-                             ('anti_dj_half', self.sources.get('dj'))):
+                             ('anti_dj_half', self._jump_source())):
                 if getattr(src, 'antithetic', False):
                     if self.path_offset:
                         raise NotImplementedError(

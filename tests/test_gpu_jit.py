@@ -176,3 +176,25 @@ def test_preset_component_counts_beyond_the_precompiled_ones():
     P((0., 1.))
     z = P._last_run.dump[0]['dW'].cpu().numpy()[0]
     assert np.abs(np.corrcoef(z) - c).max() < 5/np.sqrt(50_000)
+
+
+def test_traced_sde_with_plain_poisson_differential():
+    """'dn' differentials in user SDEs (reference tests/test_integrator.py:
+    dn/dj sources): Philox counts have the right law; replay is exact."""
+    m = sd()
+
+    @m.integrate(q=0, sources={'dt', 'dn'})
+    def counter(t, x, c=1.):
+        return {'dt': 0., 'dn': c}
+
+    paths = 200_000
+    x = np.asarray(counter(paths=paths, steps=51, x0=0., c=2., lam=3., seed=1)((0., 1.)))[-1]
+    assert np.array_equal(x, np.round(x)) and (x % 2 == 0).all()      # multiples of c
+    assert abs(x.mean()/2 - 3.) < 5*np.sqrt(3/paths)
+    assert abs(x.var()/4 - 3.) < 8*3*np.sqrt(2/paths)
+    # replay: a recorded table of counts drives the same equation
+    rng = np.random.default_rng(0)
+    dn = rng.poisson(.06, size=(50, 300))
+    y = np.asarray(counter(paths=300, steps=51, x0=0., c=2.,
+                           dn=m.replay_source(dn))((0., 1.)))[-1]
+    assert np.array_equal(y, 2.*dn.sum(axis=0))
