@@ -304,6 +304,18 @@ def _compile(source, name):
     return handle.value
 
 
+# general entry + lean entry (Philox, one constant-bank record; own register budget)
+JIT_ENTRIES = [
+    'extern "C" __global__ void __launch_bounds__(SDEB_THREADS, 1)',
+    'sdeb_jit_entry(const sdeb::KArgs a) { sdeb::integrate_body<sdeb::UserModel, false>(a); }',
+    'extern "C" __global__ void __launch_bounds__(SDEB_THREADS, 1)',
+    'sdeb_jit_entry_lean(const sdeb::KArgs a) {',
+    '    if (sdeb::UserModel::NPC + (sdeb::UserModel::NDW > 1 ? sdeb::UserModel::NDW *',
+    '        (sdeb::UserModel::NDW + 1) / 2 : 0) <= sdeb::MAX_CBANK_PARAMS)',
+    '        sdeb::integrate_body<sdeb::UserModel, true>(a);',
+    '}',
+    '']
+
 PRESET_FUNCTORS = {
     _lib.MODEL_LINEAR: 'LinearSDE<%d, false, false>',
     _lib.MODEL_LINEAR_LOG: 'LinearSDE<%d, true, false>',
@@ -327,9 +339,7 @@ def instantiate_preset(model, ncomp):
         'extern "C" __constant__ int sdeb_jit_dims[6] = {',
         '    sdeb::UserModel::NW, sdeb::UserModel::NDW, sdeb::UserModel::NX,',
         '    sdeb::UserModel::NPC, sdeb::UserModel::NCNT, sdeb::UserModel::JUMPS};',
-        'extern "C" __global__ void __launch_bounds__(SDEB_THREADS, 1)',
-        'sdeb_jit_entry(const sdeb::KArgs a) { sdeb::integrate_body<sdeb::UserModel, false>(a); }',
-        ''])
+        ''] + JIT_ENTRIES)
     return _compile(engine_source() + src, 'preset_%d_%d' % (model, ncomp))
 
 
@@ -573,9 +583,7 @@ def _model_source(nw, ndw, npc, jumps, jp_stride, jp_off, body, log, loop):
               '    }', '};', '}',
               'extern "C" __constant__ int sdeb_jit_dims[6] = {%d, %d, %d, %d, %d, %d};'
               % (nw, ndw, nw, npc, nw if jumps else 0, int(jumps)),
-              'extern "C" __global__ void __launch_bounds__(SDEB_THREADS, 1)',
-              'sdeb_jit_entry(const sdeb::KArgs a) { sdeb::integrate_body<sdeb::UserModel, false>(a); }',
-              '']
+              ''] + JIT_ENTRIES
     return '\n'.join(lines)
 
 

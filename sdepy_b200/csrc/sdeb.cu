@@ -56,7 +56,7 @@ extern "C" int sdeb_device_info(int64_t* sm_count, int64_t* cc_major, int64_t* c
 // ---------------------------------------------------------------------------
 struct JitModule {
     cudaLibrary_t lib;
-    cudaKernel_t kernel;
+    cudaKernel_t kernel, kernel_lean;
     ModelInfo mi;
 };
 static std::mutex g_jit_mutex;
@@ -822,6 +822,11 @@ extern "C" int sdeb_jit_compile(const char* source, const char* model_type, int6
     CUDA_TRY(cudaMemcpy(dims, dptr, sizeof dims, cudaMemcpyDeviceToHost));
     jm.mi.fn = (const void*)jm.kernel;
     jm.mi.fn_lean = NULL;
+    if (cudaLibraryGetKernel(&jm.kernel_lean, jm.lib, "sdeb_jit_entry_lean") == cudaSuccess &&
+        dims[3] + (dims[1] > 1 ? dims[1] * (dims[1] + 1) / 2 : 0) <= MAX_CBANK_PARAMS)
+        jm.mi.fn_lean = (const void*)jm.kernel_lean;
+    else
+        cudaGetLastError();
     jm.mi.nw = dims[0]; jm.mi.ndw = dims[1]; jm.mi.nx = dims[2]; jm.mi.npc = dims[3];
     jm.mi.ncnt = dims[4]; jm.mi.jumps = dims[5];
     std::lock_guard<std::mutex> lock(g_jit_mutex);
