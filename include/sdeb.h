@@ -213,6 +213,13 @@ int sdeb_draw_wiener(double* out, int64_t n_groups, int64_t ndw, int64_t n_paths
                      double sqrt_abs_dt, const double* chol /* device, NULL = iid */,
                      void* stream);
 
+/* Wiener source with memory (true_wiener_source.new_outside / new_inside,
+ * infrastructure.py:2460-2499): out = M1 w1 + M2 w2 + Ly z with fresh iid normals z;
+ * mats = device array [3][ndw][ndw] (M1, M2, Ly row-major), w2 may be NULL. */
+int sdeb_bridge_wiener(double* out, const double* w1, const double* w2, const double* mats,
+                       int64_t n_groups, int64_t ndw, int64_t n_paths, int64_t pitch,
+                       int64_t path_offset, uint64_t seed, int64_t step, void* stream);
+
 /* compound-Poisson draw (cpoisson_source.__call__, infrastructure.py:2017) */
 int sdeb_draw_cpoisson(double* dj, int64_t* dn, int64_t n_lanes, int64_t n_paths,
                        int64_t pitch, int64_t path_offset, uint64_t seed, int64_t step,

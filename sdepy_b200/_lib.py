@@ -77,6 +77,7 @@ def _load():
     lib.sdeb_antithetic_fold.argtypes = [ptr, i64, i64, i64, i64, i64, ptr, ptr]
     lib.sdeb_draw_wiener.argtypes = [ptr, i64, i64, i64, i64, i64, u64, i64,
                                      f64, ptr, ptr]
+    lib.sdeb_bridge_wiener.argtypes = [ptr, ptr, ptr, ptr, i64, i64, i64, i64, i64, u64, i64, ptr]
     lib.sdeb_draw_cpoisson.argtypes = [ptr, ptr, i64, i64, i64, i64, u64, i64,
                                        f64, i64, i64, f64, f64, f64, ptr]
     lib.sdeb_test_normals.argtypes = [u64, i64, ptr, ptr, ptr]
@@ -95,7 +96,7 @@ lib = _load()
 EXPORTS = ('sdeb_abi_version', 'sdeb_last_error', 'sdeb_device_info',
            'sdeb_plan', 'sdeb_integrate', 'sdeb_moments_workspace',
            'sdeb_moments', 'sdeb_histogram', 'sdeb_antithetic_fold', 'sdeb_path_eval_workspace', 'sdeb_path_cdf',
-           'sdeb_path_chf', 'sdeb_path_interp', 'sdeb_draw_wiener',
+           'sdeb_path_chf', 'sdeb_path_interp', 'sdeb_draw_wiener', 'sdeb_bridge_wiener',
            'sdeb_draw_cpoisson', 'sdeb_test_normals', 'sdeb_test_philox',
            'sdeb_fp64_peak', 'sdeb_jit_compile', 'sdeb_jit_release')
 

@@ -599,6 +599,62 @@ extern "C" int sdeb_draw_wiener(double* out, int64_t n_groups, int64_t ndw, int6
     return SDEB_OK;
 }
 
+// Brownian bridge / extension step of a Wiener source with memory
+// (true_wiener_source.new_outside / new_inside, infrastructure.py:2460-2499):
+//   out = M1 w1 + M2 w2 + Ly z,   z iid N(0,1) from Philox (counter = path, group, step)
+// with ndw x ndw matrices mats[3][ndw][ndw] (row-major; M2 ignored when w2 == NULL).
+__global__ void __launch_bounds__(256)
+bridge_wiener_kernel(const NrmK nk, double* out, const double* w1, const double* w2,
+                     const double* mats, int ndw, int64_t n_paths, int64_t pitch,
+                     int64_t path_offset, u64 seed, u32 step) {
+    __shared__ double tab[TAB_DOUBLES];
+    __shared__ double s_m[3 * 32 * 32];
+    fill_tables(tab);
+    for (int i = threadIdx.x; i < 3 * ndw * ndw; i += blockDim.x) s_m[i] = mats[i];
+    __syncthreads();
+    const int64_t path = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (path >= n_paths) return;
+    const u64 gpath = (u64)(path_offset + path);
+    u32 rk[20];
+    philox_round_keys(seed, rk);
+    Rng rng;
+    rng.rk = rk;
+    rng.c_x = (u32)gpath; rng.c_y = ((u32)(gpath >> 32) & 0xFFu) | ((u32)g << 8);
+    rng.step = step;
+    double z[34];
+    for (int b = 0; b < (ndw + 1) / 2; ++b) {
+        U4 w = rng.block((u32)b);
+        normal_pair(w, tab, nk, 1.0, z[2*b], z[2*b + 1]);
+    }
+    const double* M1 = s_m; const double* M2 = s_m + ndw * ndw; const double* Ly = s_m + 2 * ndw * ndw;
+    for (int r = 0; r < ndw; ++r) {
+        double acc = 0.0;
+        for (int c = 0; c < ndw; ++c) {
+            int64_t at = ((int64_t)g * ndw + c) * pitch + path;
+            acc += M1[r * ndw + c] * w1[at];
+            if (w2) acc += M2[r * ndw + c] * w2[at];
+            acc += Ly[r * ndw + c] * z[c];
+        }
+        out[((int64_t)g * ndw + r) * pitch + path] = acc;
+    }
+}
+
+extern "C" int sdeb_bridge_wiener(double* out, const double* w1, const double* w2,
+                                  const double* mats, int64_t n_groups, int64_t ndw,
+                                  int64_t n_paths, int64_t pitch, int64_t path_offset,
+                                  uint64_t seed, int64_t step, void* stream_) {
+    if (!out || !w1 || !mats || n_groups < 1 || n_groups > 65535 || ndw < 1 || ndw > 32 ||
+        n_paths < 1 || pitch < n_paths)
+        return fail(SDEB_EINVAL, "sdeb_bridge_wiener: bad arguments (ndw <= 32)");
+    static const NrmK nk = {SDEB_NRMK_VALUES};
+    dim3 grid((unsigned)((n_paths + 255) / 256), (unsigned)n_groups);
+    bridge_wiener_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(
+        nk, out, w1, w2, mats, (int)ndw, n_paths, pitch, path_offset, seed, (u32)step);
+    CUDA_TRY(cudaGetLastError());
+    return SDEB_OK;
+}
+
 __global__ void __launch_bounds__(256)
 draw_cpoisson_kernel(const NrmK nk, double* dj, i64* dn, int64_t n_paths, int64_t pitch, int64_t path_offset,
                      u64 seed, u32 step, double lamdt, double explam, int sign, int law,

@@ -883,6 +883,124 @@ class even_cpoisson_source(cpoisson_source):
         return np.concatenate((z, z), axis=-1)
 
 
+class true_wiener_source(source):
+    """dw with memory (reference infrastructure.py:2182-2499): ``dw(t)`` is the
+    realised value at time ``t`` of a Wiener path with ``dw(t0) = z0``, and
+    ``dw(t, dt) = dw(t + dt) - dw(t)``; new values are drawn conditionally on
+    all previously realised ones (extension beyond the known times, Brownian
+    bridge between them -- matrix bridge for time-dependent correlations,
+    2475-2499), so the SAME driving path can be integrated on different step
+    grids.  The realisations live in HBM; calls return CUDA tensors shaped
+    ``t.shape + vshape + (paths,)``."""
+
+    def __init__(self, *, paths=1, vshape=(), dtype=None, rng=None, corr=None,
+                 rho=None, rtol='max', t0=0., z0=0., seed=None, device=None):
+        super().__init__(paths=paths, vshape=vshape, dtype=dtype, rng=rng, seed=seed)
+        self._w = wiener_source(paths=paths, vshape=vshape, dtype=dtype, rng=rng,
+                                corr=corr, rho=rho, seed=self.seed)
+        self.corr = self._w.corr
+        self.rtol = np.finfo(float).resolution if rtol == 'max' else float(rtol)
+        self.t0, self.z0 = float(t0), z0
+        self._device = device
+        self._tlist, self._zlist = [self.t0], None
+        self._key = _splitmix64(self.seed)
+        self._count = 0
+
+    # lanes: groups x ndw as in wiener_source
+    def _geometry(self):
+        vs = self.vshape
+        if self.corr is not None:
+            return int(np.prod(vs[:-1], dtype=int)), vs[-1]
+        return int(np.prod(vs, dtype=int)), 1
+
+    def _init(self):
+        if self._zlist is None:
+            dev = _cuda.device(self._device)
+            groups, ndw = self._geometry()
+            z0 = np.broadcast_to(np.asarray(self.z0, dtype=float),
+                                 self.vshape + (self.paths,)).reshape(groups*ndw, self.paths)
+            self._zlist = [_cuda.to_device(z0, dev)]
+
+    def _corr_at(self, t):
+        groups, ndw = self._geometry()
+        if self.corr is None:
+            return np.eye(ndw)
+        c = np.asarray(self.corr(t) if callable(self.corr) else self.corr, dtype=float)
+        return c[..., 0] if c.ndim == 3 else c
+
+    def _launch(self, w1, w2, M1, M2, cov):
+        groups, ndw = self._geometry()
+        dev = w1.device
+        Ly = _chol(cov) if np.any(cov) else np.zeros((ndw, ndw))
+        mats = _cuda.to_device(np.stack((M1, M2, Ly)), dev)
+        out = _cuda.empty((groups*ndw, self.paths), dev)
+        self._count += 1
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.sdeb_bridge_wiener(
+                _cuda.ptr(out), _cuda.ptr(w1), _cuda.ptr(w2), _cuda.ptr(mats), groups,
+                ndw, self.paths, self.paths, 0, self._key, self._count,
+                _cuda.stream_ptr(dev)))
+        return out
+
+    def new_outside(self, w, t, s):
+        """Value at ``s`` beyond the known times, given ``w`` at the nearest
+        known time ``t``; covariance ``corr((t+s)/2)*|s-t|`` (reference 2460-2469)."""
+        ndw = self._geometry()[1]
+        eye = np.eye(ndw)
+        return self._launch(w, None, eye, 0*eye, self._corr_at((t + s)/2)*abs(s - t))
+
+    def new_inside(self, w1, w2, t1, t2, s):
+        """Bridge value at ``t1 < s < t2`` (reference 2475-2499)."""
+        t0 = self.t0
+        if t2 <= t0:
+            w1, w2, t1, t2 = w2, w1, t2, t1
+        ndw = self._geometry()[1]
+        eye = np.eye(ndw)
+        a, b = s - t1, t2 - s
+        if callable(self.corr):
+            A, B = self._corr_at((t1 + s)/2)*a, self._corr_at((s + t2)/2)*b
+            Z = B @ np.linalg.inv(A + B)
+            return self._launch(w1, w2, Z, eye - Z, (Z @ A)*np.sign(a))
+        z = b/(a + b)
+        return self._launch(w1, w2, z*eye, (1 - z)*eye, self._corr_at(s)*abs(z*a))
+
+    def _value(self, s):
+        import bisect
+        self._init()
+        t, z = self._tlist, self._zlist
+        k = bisect.bisect_right(t, s)
+        if k > 0 and np.isclose(s, t[k - 1], rtol=self.rtol, atol=0.):
+            return z[k - 1]
+        if k == len(t):
+            z.append(self.new_outside(z[-1], t[-1], s)); t.append(s)
+            return z[-1]
+        if k == 0:
+            z.insert(0, self.new_outside(z[0], t[0], s)); t.insert(0, s)
+            return z[0]
+        z.insert(k, self.new_inside(z[k - 1], z[k], t[k - 1], t[k], s)); t.insert(k, s)
+        return z[k]
+
+    def _values(self, s):
+        s = np.asarray(s, dtype=float)
+        rows = [self._value(float(v)) for v in s.reshape(-1)]
+        out = torch.stack(rows) if rows else None
+        return out.reshape(s.shape + self.vshape + (self.paths,))
+
+    def __call__(self, t, dt=None):
+        if dt is None:
+            return self._values(t)
+        t, dt = np.broadcast_arrays(t, dt)
+        return self._values(t + dt) - self._values(t)
+
+    @property
+    def size(self):
+        return 0 if self._zlist is None else sum(z.numel() for z in self._zlist)
+
+    @property
+    def t(self):
+        return np.array(self._tlist, dtype=float)
+
+
 class replay_source:
     """Replay-mode source: a table of pre-drawn increments, one entry per
     integration step, e.g. the increments logged from the reference's own

@@ -219,3 +219,53 @@ def test_path_dependent_and_process_valued_parameters():
     a = np.where(np.arange(20_000) % 2, 1., -1.)
     y = np.asarray(f(paths=20_000, steps=11, x0=0., a=a, s=.1, seed=2)((0., 1.)))[-1]
     assert abs(y[1::2].mean() - 1.) < .01 and abs(y[0::2].mean() + 1.) < .01
+
+
+def test_true_wiener_source_memory_bridge_and_convergence():
+    """Wiener source with memory on the device (reference infrastructure.py:
+    2379-2499, tests/test_source.py:286-410): repeated calls agree, bridged
+    values have Brownian covariances, and the same driving path integrated on
+    nested grids converges strongly (doc/quickguide.rst:268-294)."""
+    m = sd()
+    paths = 100_000
+    dw = m.true_wiener_source(paths=paths, vshape=(2,), rho=.5, seed=7)
+    w1 = dw(1.).cpu().numpy()
+    assert w1.shape == (2, paths)
+    assert np.array_equal(dw(1.).cpu().numpy(), w1)               # memory
+    assert np.array_equal(dw(0.).cpu().numpy(), np.zeros((2, paths)))
+    w05 = dw(.5).cpu().numpy()                                    # bridge between 0 and 1
+    w2 = dw(2.).cpu().numpy()                                     # extension
+    w15 = dw(1.5).cpu().numpy()                                   # bridge between 1 and 2
+    assert np.array_equal(dw(.5, 1.).cpu().numpy(), w15 - w05)
+    assert list(dw.t) == [0., .5, 1., 1.5, 2.] and dw.size == 5*2*paths
+    se = 5/np.sqrt(paths)
+    for a, ta in ((w05, .5), (w1, 1.), (w15, 1.5), (w2, 2.)):
+        assert abs(a[0].var()/ta - 1) < se*np.sqrt(2) and abs(np.corrcoef(a)[0, 1] - .5) < se
+        for b, tb in ((w05, .5), (w1, 1.), (w15, 1.5), (w2, 2.)):
+            cov = np.mean(a[0]*b[0])
+            assert abs(cov - min(ta, tb)) < se*np.sqrt(ta*tb + min(ta, tb)**2)
+    # increments over disjoint intervals are uncorrelated
+    assert abs(np.corrcoef(w05[1], (w1 - w05)[1])[0, 1]) < se
+    # time-dependent correlation: matrix bridge keeps unit variances per unit time
+    dwt = m.true_wiener_source(paths=paths, vshape=(2,), seed=8,
+                               corr=lambda t: np.array(((1., .2 + .3*t), (.2 + .3*t, 1.))))
+    e1, emid = dwt(1.).cpu().numpy(), dwt(.4).cpu().numpy()
+    assert abs(emid[0].var()/.4 - 1) < 2*se and abs((e1 - emid)[1].var()/.6 - 1) < 2*se
+    assert abs(np.corrcoef(emid)[0, 1] - (.2 + .3*.2)) < 2*se
+    # convergence study: one Brownian path, nested grids, exact lognormal solution
+    tw = m.true_wiener_source(paths=20_000, seed=9)
+    errs = []
+    for n in (4, 16, 64):
+        x = m.lognorm_process(paths=20_000, steps=n + 1, x0=1., mu=.05, sigma=.5, dw=tw)((0., 1.))
+        # Euler on log x is exact for constant parameters: identical terminal values
+        errs.append(np.asarray(x)[-1])
+    wT = tw(1.).cpu().numpy()
+    exact = np.exp((.05 - .125) + .5*wT)
+    for e in errs:
+        assert np.allclose(e, exact, rtol=1e-12)
+
+    def f(t, x, mu=.05, sigma=.5):
+        return {'dt': mu*x, 'dw': sigma*x}
+    strong = [np.abs(np.asarray(m.integrate(f)(paths=20_000, steps=n + 1, x0=1., dw=tw)((0., 1.)))[-1]
+                     - exact).mean() for n in (4, 16, 64)]
+    assert strong[0] > 1.6*strong[1] > 2.5*strong[2]              # ~ sqrt(dt) strong order
