@@ -1185,6 +1185,71 @@ class montecarlo:
                     'total number of cumulated paths inconsistent with stored '
                     'cumulated counts')
 
+    def allreduce(self, group=None):
+        """Merge the statistics cumulated by every rank (paths sharded across
+        GPUs): ONE all-reduce (SUM) of the packed vector -- path count, mean,
+        the four moments re-centred on a common constant (rank 0's centre,
+        shifted binomially), histogram bins and the out-of-range counts.  All
+        ranks must use the same bin edges (pass explicit ``bins`` edges or an
+        integer ``bins`` with a ``range``).  NCCL when the process group is
+        NCCL, gloo on CPU.  Returns self (updated in place on every rank)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or self.paths == 0:
+            return self
+        backend = dist.get_backend(group)
+        dev = (torch.device('cuda', torch.cuda.current_device())
+               if backend == 'nccl' else torch.device('cpu'))
+        rank = dist.get_rank(group)
+        vshape = self.vshape
+        # common centre and (if any) common edges: taken from rank 0
+        head = [np.asarray(self._center, dtype=float).ravel()]
+        has_hist = self._counts is not None
+        if has_hist:
+            head += [np.asarray(e, dtype=float) for e in self._edges]
+        ref = torch.from_numpy(np.concatenate(head)).to(dev)
+        mine = ref.clone()
+        dist.broadcast(ref, src=dist.get_global_rank(group, 0) if group is not None else 0,
+                       group=group)
+        ref_np = ref.cpu().numpy()
+        nc = int(np.prod(vshape, dtype=int))
+        c0 = ref_np[:nc].reshape(vshape)
+        if has_hist and not np.array_equal(ref_np[nc:], mine.cpu().numpy()[nc:]):
+            raise ValueError('montecarlo.allreduce: ranks use different histogram '
+                             'bins; pass explicit edges or bins=int with range=')
+        # moments about c0:  E[(x-c0)^k] = sum_j C(k,j) (c-c0)^(k-j) E[(x-c)^j]
+        from math import comb
+        d = np.asarray(self._center, dtype=float) - c0
+        m = [np.ones(vshape)] + [np.asarray(mm, dtype=float) for mm in self._moments]
+        shifted = [sum(comb(k, j)*d**(k - j)*m[j] for j in range(k + 1)) for k in range(1, 5)]
+        n = float(self.paths)
+        parts = [np.array([n])] + [n*np.asarray(self._mean, dtype=float).ravel()] + [
+            n*sk.ravel() for sk in shifted]
+        if has_hist:
+            parts += [np.asarray(c, dtype=float) for c in
+                      (self._counts[i] for i in np.ndindex(vshape))]
+            parts += [np.asarray(self._paths_outside, dtype=float).ravel()]
+        buf = torch.from_numpy(np.concatenate(parts)).to(dev)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        buf = buf.cpu().numpy()
+        N = buf[0]
+        at = 1
+        self._mean[...] = (buf[at:at + nc]/N).reshape(vshape); at += nc
+        for k in range(4):
+            self._moments[k][...] = (buf[at:at + nc]/N).reshape(vshape); at += nc
+        self._center = c0.astype(self._center.dtype)
+        if has_hist:
+            for j, i in enumerate(np.ndindex(vshape)):
+                nb = len(self._edges[j]) - 1
+                tot = np.rint(buf[at:at + nb]).astype(self.ctype); at += nb
+                self._counts[i] = tot
+                self._counts_dev[j].copy_(torch.from_numpy(tot.astype(np.int64)))
+            out = np.rint(buf[at:at + nc]).astype(self.ctype).reshape(vshape)
+            self._paths_outside = out
+            for j in range(nc):
+                self._outside_dev[j].fill_(int(out.ravel()[j]))
+        self._paths[0] = int(round(N))
+        return self
+
     def __getitem__(self, i):
         a = montecarlo(bins=self._bins if self.paths == 0 else None)
         a._paths = self._paths

@@ -16,6 +16,47 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _montecarlo_state(sample, edges):
+    """A montecarlo object in the state its device update() would leave it in
+    (built with NumPy here: the CPU box has no GPU to run update())."""
+    import sdepy_b200 as sd
+    a = sd.montecarlo(bins=25)
+    vshape, m = sample.shape[:-1], sample.shape[-1]
+    a._center = sample.mean(axis=-1)
+    d = sample - a._center[..., None]
+    a._moments = tuple((d**k).mean(axis=-1) for k in (1, 2, 3, 4))
+    a._mean = sample.mean(axis=-1)
+    a._edges, a._uniform = [edges for _ in np.ndindex(vshape)], [True]*int(np.prod(vshape))
+    a._counts = np.empty(vshape, dtype=object)
+    a._bins = np.empty(vshape, dtype=object)
+    a._paths_outside = np.zeros(vshape, dtype=np.int64)
+    a._counts_dev, a._outside_dev = [], []
+    for i in np.ndindex(vshape):
+        c, _ = np.histogram(sample[i], bins=edges)
+        a._counts[i], a._bins[i] = c.astype(np.int64), edges
+        a._paths_outside[i] = m - c.sum()
+        a._counts_dev.append(torch.from_numpy(c.astype(np.int64)))
+        a._outside_dev.append(torch.tensor([m - c.sum()]))
+    a._paths[0] = m
+    return a
+
+
+def _montecarlo_merge_ok(rank, world):
+    rng = np.random.default_rng(5)
+    x = rng.lognormal(size=(2, 3000))
+    edges = np.linspace(0., 6., 26)
+    lo, hi = (0, 1300) if rank == 0 else (1300, 3000)
+    a = _montecarlo_state(x[:, lo:hi], edges).allreduce()
+    full = _montecarlo_state(x, edges)
+    ok = a.paths == 3000
+    for f in ('mean', 'var', 'std', 'skew', 'kurtosis', 'stderr'):
+        ok = ok and np.allclose(getattr(a, f)(), getattr(full, f)(), rtol=1e-10)
+    for i in range(2):
+        ok = ok and np.array_equal(a[i].histogram()[0], full[i].histogram()[0])
+        ok = ok and a[i].outpaths == full[i].outpaths
+    return bool(ok)
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -51,6 +92,7 @@ def _worker(rank, world, port, q):
         tot, out = allreduce_histogram(cts, cnt - cts.sum())
         ref, _ = np.histogram(x[0, 0], bins=edges)
         ok = ok and np.array_equal(tot, ref) and out == 0
+        ok = ok and _montecarlo_merge_ok(rank, world)
         q.put((rank, off, cnt, bool(ok)))
     finally:
         dist.destroy_process_group()
