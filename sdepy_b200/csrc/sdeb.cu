@@ -209,7 +209,6 @@ extern "C" int sdeb_integrate(const sdeb_problem* p, void* stream_) {
     if (lean) {
         // single time-invariant record: serve it from the constant bank
         for (int k = 0; k < plan.npt; ++k) a.pc[k] = p->params_host[k];
-        a.use_pc = 1;
     }
     a.n_paths = p->n_paths; a.path_offset = p->path_offset; a.pitch = p->pitch;
     a.n_steps = (int)p->n_steps; a.n_groups = (int)p->n_groups; a.n_rows = (int)p->n_rows;
