@@ -200,3 +200,39 @@ def test_time_dependent_correlation_hw3():
         c = np.corrcoef(z)
         want = HW['corr'](grid[n] + (grid[n + 1] - grid[n])/2)
         assert np.abs(c - want).max() < 5/np.sqrt(paths)
+
+
+def test_increment_stream_quality():
+    """Statistical checks of the in-kernel draws beyond the first moments:
+    distribution (KS), tails, independence across steps and across neighbouring
+    paths, independence of the two normals of a Box-Muller pair across the
+    odd/even step reuse (one-factor models keep the second normal for the next
+    step)."""
+    import scipy.stats
+    m = sd()
+    paths, n = 200_000, 64
+    P = m.wiener_process(paths=paths, steps=n + 1, seed=2025)
+    P._dump_increments = True
+    P((0., 1.))
+    z = (P._last_run.dump[0]['dW'].cpu().numpy()[:, 0, :]*np.sqrt(n))     # [n, paths] ~ N(0,1)
+    N = z.size
+    assert scipy.stats.kstest(z[::7].ravel()[:500_000], 'norm').pvalue > 1e-3
+    for thr in (2., 3., 4.):
+        p = 2*scipy.stats.norm.sf(thr)
+        k = (np.abs(z) > thr).sum()
+        assert abs(k - N*p) < 5*np.sqrt(N*p), thr
+    # moments up to 6
+    for k, want in ((2, 1.), (4, 3.), (6, 15.)):
+        se = np.sqrt((scipy.stats.norm.moment(2*k) - want**2)/N)
+        assert abs((z**k).mean() - want) < 5*se
+    se = 5/np.sqrt(paths*(n - 1))
+    assert abs(np.mean(z[1:]*z[:-1])) < se                   # lag-1 across steps (pair reuse!)
+    assert abs(np.mean(z[2:]*z[:-2])) < se
+    assert abs(np.mean(z[:, 1:]*z[:, :-1])) < se             # neighbouring paths
+    assert abs(np.mean((z[1::2]**2 - 1)*(z[0::2]**2 - 1))) < 3*se   # pair members independent
+    # two different seeds / two calls: unrelated streams
+    Q = m.wiener_process(paths=paths, steps=n + 1, seed=2026)
+    Q._dump_increments = True
+    Q((0., 1.))
+    z2 = Q._last_run.dump[0]['dW'].cpu().numpy()[:, 0, :]*np.sqrt(n)
+    assert abs(np.mean(z*z2)) < 5/np.sqrt(N)
