@@ -269,3 +269,26 @@ def test_true_wiener_source_memory_bridge_and_convergence():
     strong = [np.abs(np.asarray(m.integrate(f)(paths=20_000, steps=n + 1, x0=1., dw=tw)((0., 1.)))[-1]
                      - exact).mean() for n in (4, 16, 64)]
     assert strong[0] > 1.6*strong[1] > 2.5*strong[2]              # ~ sqrt(dt) strong order
+
+
+def test_online_statistics_every_row_and_groups():
+    """output='stats' on a full timeline and with several lane groups equals
+    the reductions of the stored paths (same seed => same paths)."""
+    m = sd()
+    tl = np.linspace(0., 1., 41)
+    kw = dict(paths=30_000, vshape=(2, 3), x0=1., mu=.02, sigma=np.array([.1, .2, .3])[:, None],
+              seed=31)
+    xd = m.lognorm_process(output='device', **kw)(tl)
+    st = m.lognorm_process(output='stats', **kw)(tl)
+    assert st.sums.shape == (41, 2, 3, 8)
+    assert np.allclose(np.asarray(st.pmean())[..., 0], np.asarray(xd.pmean())[..., 0], rtol=1e-12)
+    assert np.allclose(np.asarray(st.pvar())[1:, ..., 0], np.asarray(xd.pvar())[1:, ..., 0], rtol=1e-9)
+    assert np.array_equal(np.asarray(st.pmin())[..., 0], np.asarray(xd.pmin())[..., 0])
+    assert np.array_equal(np.asarray(st.pmax())[..., 0], np.asarray(xd.pmax())[..., 0])
+    xs = np.asarray(xd)
+    d = xs - 1.
+    assert np.allclose(np.asarray(st.skew())[5:, ..., 0],
+                       ((d - d.mean(-1, keepdims=True))**3).mean(-1)[5:]/xs.var(-1)[5:]**1.5, rtol=1e-7)
+    # too many rows x components for the in-kernel accumulators: loud failure
+    with pytest.raises(NotImplementedError):
+        m.wiener_process(paths=10, vshape=(40,), output='stats')(np.linspace(0, 1, 400))
