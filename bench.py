@@ -225,7 +225,7 @@ def run_ours(a):
 
     def make(seed):
         return sd.heston_process(paths=paths, steps=grid, rho=RHO, seed=seed,
-                                 output='stats', payoff=payoff, getinfo=False,
+                                 output='stats', payoff=payoff, getinfo=True,
                                  path_offset=rank*paths, **HESTON)
 
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -276,6 +276,7 @@ def run_ours(a):
         price = float(np.asarray(r.payoff_mean())[-1, 0])
     barrier()
     e2e_s = time.perf_counter() - t0
+    # per step: steps table, store rows, parameter record, initial state, centre
     h2d = N_STEPS*16 + N_STEPS*4 + 9*8 + 2*8 + 8
     d2h = 2*_lib.NSTAT*8
 

@@ -290,6 +290,11 @@ class resident_stats_run:
             kind, strike, scale = sde.payoff
             p.payoff_kind = {'call': _lib.PAYOFF_CALL, 'put': _lib.PAYOFF_PUT}[kind]
             p.payoff_strike, p.payoff_scale = float(strike), float(scale)
+        if sde.getinfo and spec.ncnt:
+            # per-path diagnostics (negative_y_count / jump_count), as with the
+            # reference's default getinfo=True; accumulated across launches
+            b['counter'] = _cuda.zeros((spec.groups*spec.ncnt, sde.paths), dev, torch.int64)
+            p.counter = b['counter'].data_ptr()
         plan = self.plan = _lib.plan(p)
         b['ws'] = _cuda.empty((max(plan.workspace_bytes//8, 1),), dev)
         p.workspace, p.workspace_bytes = b['ws'].data_ptr(), plan.workspace_bytes
