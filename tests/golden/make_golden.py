@@ -223,6 +223,38 @@ def main():
          mc_pdf_i=np.stack([mc1[i].pdf(xs, method='interp') for i in range(2)]),
          mc_cdf_i=np.stack([mc1[i].cdf(xs, method='interp') for i in range(2)]))
 
+    # closed forms of sdepy.analytical (reference analytical.py) at the parameter
+    # sets of tests/test_gpu_quant.py: the Philox-mode oracle values
+    A = sdepy.analytical if hasattr(sdepy, 'analytical') else __import__('sdepy.analytical').analytical
+    tq = np.array([.5, 1., 2., 3.])
+    uq = np.linspace(-2., 2., 9)
+    xq = np.linspace(-1., 2., 7)
+    wp = dict(x0=1., mu=.5, sigma=.8)
+    lp = dict(x0=1., mu=.05, sigma=.3)
+    op = dict(x0=1., theta=.3, k=1.5, sigma=.4)
+    hp = dict(x0=(.2, .1), theta=(.3, .0), k=(1., .5), sigma=(.2, .3), rho=.4)
+    cp = dict(x0=.5, theta=.3, k=1.2, xi=.3)
+    ep = dict(x0=1., mu=.05, sigma=1., y0=.04, theta=.05, k=1.5, xi=.3, rho=-.6)
+    mp = dict(x0=1., mu=.05, sigma=.2, lam=2., a=-.1, b=.15)
+    kp = dict(x0=1., mu=.05, sigma=.2, lam=2., a=.1, b=.15, pa=.4)
+    save('analytical',
+         tq=tq, uq=uq, xq=xq,
+         wiener_mean=A.wiener_mean(tq, **wp), wiener_var=A.wiener_var(tq, **wp),
+         wiener_cdf=np.stack([A.wiener_cdf(t, xq, **wp) for t in tq]),
+         wiener_chf=np.stack([A.wiener_chf(t, uq, **wp) for t in tq]),
+         lognorm_mean=A.lognorm_mean(tq, **lp), lognorm_std=A.lognorm_std(tq, **lp),
+         lognorm_cdf=np.stack([A.lognorm_cdf(t, xq[2:] + .2, **lp) for t in tq]),
+         oruh_mean=A.oruh_mean(tq, **op), oruh_var=A.oruh_var(tq, **op),
+         hw2f_mean=A.hw2f_mean(tq, **hp), hw2f_var=A.hw2f_var(tq, **hp),
+         cir_mean=A.cir_mean(tq, **cp), cir_var=A.cir_var(tq, **cp),
+         heston_log_mean=A.heston_log_mean(tq, **ep), heston_log_var=A.heston_log_var(tq, **ep),
+         heston_log_chf=np.stack([A.heston_log_chf(t, uq, **ep) for t in tq]),
+         mjd_mean=A.mjd_mean(tq, **mp),
+         mjd_log_chf=np.stack([A.mjd_log_chf(t, uq, **mp) for t in tq]),
+         kou_mean=A.kou_mean(tq, **kp),
+         kou_log_chf=np.stack([A.kou_log_chf(t, uq, **kp) for t in tq]),
+         bscall=A.bscall(1.1, tq, x0=1., r=.03, sigma=.25), bsput=A.bsput(1.1, tq, x0=1., r=.03, sigma=.25))
+
     # the reference's own known-answer check: Euler on log x is exact for
     # constant-parameter lognormal on shared increments
     # (sdepy/tests/test_processes.py:681-708)
