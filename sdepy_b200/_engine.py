@@ -67,13 +67,18 @@ class problem_spec:
         self.nchol = self.npt - self.npc
 
 
+_TRIL = {}
+
+
 def chol_entries(L, ndw):
     """Row-major lower triangle of a Cholesky factor (identity if None)."""
     if ndw <= 1:
         return np.zeros(0)
+    if ndw not in _TRIL:
+        _TRIL[ndw] = np.tril_indices(ndw)
     if L is None:
         L = np.eye(ndw)
-    return np.asarray(L, dtype=float)[np.tril_indices(ndw)]
+    return np.asarray(L, dtype=float)[_TRIL[ndw]]
 
 
 def assemble_records(blocks, spec):

@@ -757,6 +757,8 @@ def lane_values(z, lead_shape, what='parameter', paths=None):
     given, one row per lane, shape ``[lanes, paths]``."""
     z = np.asarray(z, dtype=float)
     lead = tuple(lead_shape)
+    if z.size == 1:                       # scalar: the common case, no broadcasting machinery
+        return np.full(int(np.prod(lead, dtype=int)), z.reshape(-1)[0])
     try:
         return np.broadcast_to(z, lead + (1,)).reshape(-1).copy()
     except ValueError:
