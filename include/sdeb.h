@@ -198,6 +198,35 @@ int sdeb_path_interp(const double* y_lo, const double* y_hi, double w_lo, double
                      int64_t n_paths, double* out, void* stream);
 
 /*
+ * Reductions along an inner axis of a resident slab x[outer][n_reduce][cols]
+ * (cols contiguous), one output per (outer, col): process.tmin/tmax/tsum/tmean/
+ * tvar/tstd (outer = 1, n_reduce = time points; infrastructure.py:963-1030) and
+ * vmin..vstd (outer = time points, n_reduce = values, cols = paths; 894-960).
+ * Each output pointer may be NULL.  The sum S accumulates in index order (bit-equal
+ * to NumPy's reduction of a non-contiguous axis); out_sum = S / sum_div (1 for the
+ * sum, n_reduce for the mean); out_ssd = sum of (x - S/n_reduce)^2, divided by
+ * ssd_div (n_reduce - ddof: numpy.var) and square-rooted when ssd_sqrt != 0
+ * (numpy.std).  NaNs propagate through min / max as in NumPy.
+ */
+int sdeb_axis_reduce(const double* x, int64_t outer, int64_t n_reduce, int64_t cols,
+                     double* out_min, double* out_max, double* out_sum, double* out_ssd,
+                     double sum_div, double ssd_div, int64_t ssd_sqrt, void* stream);
+
+/*
+ * Scans along the time axis of x[rows][cols] (infrastructure.py:990-997, 1032-1122):
+ *   SDEB_SCAN_CUMSUM  out[r] = x[0] + ... + x[r]                       (tcumsum)
+ *   SDEB_SCAN_INT     out[0] = 0, out[r] = out[r-1] + x[r-1]*w[r-1]    (tint, w = dt)
+ *   SDEB_SCAN_DIFF    out[r] = (x[r+1] - x[r]) / w[r], rows-1 rows     (tdiff, w = dt**dt_exp
+ *                     or NULL for plain increments)
+ * weights: device array of rows-1 doubles.
+ */
+#define SDEB_SCAN_CUMSUM 0
+#define SDEB_SCAN_INT    1
+#define SDEB_SCAN_DIFF   2
+int sdeb_time_scan(const double* x, int64_t rows, int64_t cols, int64_t mode,
+                   const double* weights, double* out, void* stream);
+
+/*
  * 1-D histogram of x[n] on given edges[nbins+1] with numpy.histogram
  * semantics (half-open bins, last one closed; montecarlo._update_histogram,
  * infrastructure.py:2961-3021).  counts[nbins] and outside[1] are

@@ -259,6 +259,40 @@ def generic_replay(sde, params, x0, grid, where, dW, log=False,
     return np.exp(xx) if log else xx
 
 
+def system_replay(sde, q, params, x0s, grid, where, dW, addaxis):
+    """Replay driver for a user system ``sde(t, x1..xq, **params) -> (dict,)*q``
+    (``SDEs``, integration.py:1584-1835).  The q equations are stacked along a
+    new axis -2 (``addaxis``) or along the last axis of vshape, equation k
+    owning ``[k*d, (k+1)*d)`` (unpack/pack, integration.py:1735-1777); the
+    stacked coefficients then go through the plain Euler update (718)."""
+    grid = np.asarray(grid, dtype=float)
+    out_of = {int(j): i for i, j in enumerate(where)}
+    dW = np.asarray(dW)
+    wshape, paths = dW.shape[1:-1], dW.shape[-1]
+    if addaxis:
+        vshape = wshape[:-1]
+        unpack = lambda X: tuple(X[..., k, :] for k in range(q))
+        idx = np.index_exp[..., np.newaxis, :]
+    else:
+        d = wshape[-1]//q
+        vshape = wshape[:-1] + (d,)
+        unpack = lambda X: tuple(X[..., k*d:(k + 1)*d, :] for k in range(q))
+        idx = np.index_exp[...]
+    pack = lambda zs: np.concatenate(
+        tuple(np.broadcast_to(z, vshape + (paths,))[idx] for z in zs), axis=-2)
+    X = pack(tuple(np.asarray(z, dtype=float) for z in x0s))
+    rows = [X.copy()] if 0 in out_of else []
+    for n in range(grid.size - 1):
+        s, ds = grid[n], grid[n+1] - grid[n]
+        As = sde(s, *unpack(X), **_at(params, s))
+        ids = sorted(set().union(*(a.keys() for a in As)))
+        terms = [(pack(tuple(a.get(k, 0) for a in As)), k) for k in ids]
+        X = _euler_sum(X, terms, {'dt': ds, 'dw': dW[n]})
+        if n + 1 in out_of:
+            rows.append(X.copy())
+    return tuple(np.stack([unpack(r)[k] for r in rows]) for k in range(q))
+
+
 def milstein(x, terms, dz, b_dx):
     """Milstein update ``x + a ds + b dw + (1/2) b b' (dw^2 - ds)``.
 

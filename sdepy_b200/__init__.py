@@ -22,5 +22,19 @@ from .integration import (                           # noqa: F401
     jumpdiff_SDE, jumpdiff_process,
     merton_jumpdiff_SDE, merton_jumpdiff_process,
     kou_jumpdiff_SDE, kou_jumpdiff_process)
+from .kfun import kfunc, iskfunc                     # noqa: F401
+
+# interactive shortcuts, wrapped as kfuncs (reference shortcuts.py:73-99 with
+# the default _config.KFUNC = 'shortcuts': full names stay plain classes)
+dw, dn, dj = kfunc(wiener_source), kfunc(poisson_source), kfunc(cpoisson_source)
+odd_dw, even_dn, even_dj = (kfunc(odd_wiener_source), kfunc(even_poisson_source),
+                            kfunc(even_cpoisson_source))
+true_dw = kfunc(true_wiener_source)
+wiener, lognorm = kfunc(wiener_process), kfunc(lognorm_process)
+oruh, cir = kfunc(ornstein_uhlenbeck_process), kfunc(cox_ingersoll_ross_process)
+hwff, hw1f = kfunc(hull_white_process), kfunc(hull_white_1factor_process)
+heston_xy, heston = kfunc(full_heston_process), kfunc(heston_process)
+jumpdiff = kfunc(jumpdiff_process)
+mjd, kou = kfunc(merton_jumpdiff_process), kfunc(kou_jumpdiff_process)
 
 __version__ = '0.1.0'

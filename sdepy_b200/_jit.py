@@ -365,7 +365,7 @@ class _traced:
         return 1 if self._system else self._lanes()[1]
 
     def _param_target(self):
-        return self.wshape[:-1] if self._system else self.wshape
+        return self.vshape if self._system else self.wshape
 
     def _trace(self, t):
         """Call the user's sde at time t with symbolic variables.  Returns

@@ -74,6 +74,8 @@ def _load():
     lib.sdeb_path_cdf.argtypes = [ptr, ptr, f64, f64, i64, i64, ptr, i64, ptr, ptr]
     lib.sdeb_path_chf.argtypes = [ptr, ptr, f64, f64, i64, i64, ptr, i64, ptr, ptr, i64, ptr]
     lib.sdeb_path_interp.argtypes = [ptr, ptr, f64, f64, i64, ptr, ptr]
+    lib.sdeb_axis_reduce.argtypes = [ptr, i64, i64, i64, ptr, ptr, ptr, ptr, f64, f64, i64, ptr]
+    lib.sdeb_time_scan.argtypes = [ptr, i64, i64, i64, ptr, ptr, ptr]
     lib.sdeb_antithetic_fold.argtypes = [ptr, i64, i64, i64, i64, i64, ptr, ptr]
     lib.sdeb_draw_wiener.argtypes = [ptr, i64, i64, i64, i64, i64, u64, i64,
                                      f64, ptr, ptr]
@@ -96,9 +98,12 @@ lib = _load()
 EXPORTS = ('sdeb_abi_version', 'sdeb_last_error', 'sdeb_device_info',
            'sdeb_plan', 'sdeb_integrate', 'sdeb_moments_workspace',
            'sdeb_moments', 'sdeb_histogram', 'sdeb_antithetic_fold', 'sdeb_path_eval_workspace', 'sdeb_path_cdf',
-           'sdeb_path_chf', 'sdeb_path_interp', 'sdeb_draw_wiener', 'sdeb_bridge_wiener',
+           'sdeb_path_chf', 'sdeb_path_interp', 'sdeb_axis_reduce', 'sdeb_time_scan', 'sdeb_draw_wiener', 'sdeb_bridge_wiener',
            'sdeb_draw_cpoisson', 'sdeb_test_normals', 'sdeb_test_philox',
            'sdeb_fp64_peak', 'sdeb_jit_compile', 'sdeb_jit_release')
+
+
+SCAN_CUMSUM, SCAN_INT, SCAN_DIFF = 0, 1, 2
 
 
 def check(rc):

@@ -489,6 +489,181 @@ extern "C" int sdeb_path_interp(const double* y_lo, const double* y_hi, double w
 }
 
 // ---------------------------------------------------------------------------
+// reductions and scans along an inner axis of a resident slab
+// x is [outer][R][cols] (cols contiguous): process.tmin/tmax/tsum/tmean/tvar
+// (outer = 1, R = time points, cols = values x paths; infrastructure.py:
+// 963-1030) and vmin..vvar (outer = time points, R = values, cols = paths;
+// 894-960).  One thread owns one (outer, col) column and walks R in order:
+// NumPy reduces a non-contiguous axis sequentially, so sums are bit-equal.
+// HBM-bound: 8 independent loads in flight per thread.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double np_min(double a, double v) { return (v < a || v != v) ? v : a; }
+__device__ __forceinline__ double np_max(double a, double v) { return (v > a || v != v) ? v : a; }
+
+__global__ void __launch_bounds__(256)
+axis_reduce_kernel(const double* __restrict__ x, int64_t outer, int64_t R, int64_t cols,
+                   double* omin, double* omax, double* osum, double* ossd,
+                   double sum_div, double ssd_div, int ssd_sqrt) {
+    const int64_t total = outer * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o = i / cols, c = i - o * cols;
+        const double* col = x + o * R * cols + c;
+        double first = col[0];
+        double mn = first, mx = first, sum = first;
+        int64_t r = 1;
+        for (; r + 8 <= R; r += 8) {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = col[(r + k) * cols];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                mn = np_min(mn, v[k]); mx = np_max(mx, v[k]); sum = __dadd_rn(sum, v[k]);
+            }
+        }
+        for (; r < R; ++r) {
+            double v = col[r * cols];
+            mn = np_min(mn, v); mx = np_max(mx, v); sum = __dadd_rn(sum, v);
+        }
+        if (omin) omin[i] = mn;
+        if (omax) omax[i] = mx;
+        if (osum) osum[i] = __ddiv_rn(sum, sum_div);
+        if (ossd) {
+            // numpy.var: mean = sum/R, then add.reduce((x - mean)*(x - mean))
+            const double mean = __ddiv_rn(sum, (double)R);
+            double d = __dsub_rn(first, mean);
+            double acc = __dmul_rn(d, d);
+            r = 1;
+            for (; r + 8 <= R; r += 8) {
+                double v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = col[(r + k) * cols];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    d = __dsub_rn(v[k], mean);
+                    acc = __dadd_rn(acc, __dmul_rn(d, d));
+                }
+            }
+            for (; r < R; ++r) {
+                d = __dsub_rn(col[r * cols], mean);
+                acc = __dadd_rn(acc, __dmul_rn(d, d));
+            }
+            acc = __ddiv_rn(acc, ssd_div);
+            ossd[i] = ssd_sqrt ? __dsqrt_rn(acc) : acc;
+        }
+    }
+}
+
+extern "C" int sdeb_axis_reduce(const double* x, int64_t outer, int64_t n_reduce, int64_t cols,
+                                double* out_min, double* out_max, double* out_sum,
+                                double* out_ssd, double sum_div, double ssd_div,
+                                int64_t ssd_sqrt, void* stream_) {
+    if (!x || outer < 1 || n_reduce < 1 || cols < 1 ||
+        !(out_min || out_max || out_sum || out_ssd))
+        return fail(SDEB_EINVAL, "sdeb_axis_reduce: bad arguments");
+    int64_t need = (outer * cols + 255) / 256;
+    int blocks = (int)(need < 2368 ? need : 2368);
+    axis_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(
+        x, outer, n_reduce, cols, out_min, out_max, out_sum, out_ssd, sum_div, ssd_div,
+        (int)ssd_sqrt);
+    CUDA_TRY(cudaGetLastError());
+    return SDEB_OK;
+}
+
+// process.tcumsum / tint / tdiff (infrastructure.py:990-997, 1032-1122) over
+// x [rows][cols]; w holds one weight per time interval (device, rows-1).
+//   SCAN_CUMSUM : out[r] = x[0] + ... + x[r]
+//   SCAN_INT    : out[0] = 0, out[r] = out[r-1] + x[r-1]*w[r-1]
+//   SCAN_DIFF   : out[r] = (x[r+1] - x[r]) (/ w[r] when w != NULL), rows-1 rows
+enum { SCAN_CUMSUM = 0, SCAN_INT = 1, SCAN_DIFF = 2 };
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+time_scan_kernel(const double* __restrict__ x, int64_t rows, int64_t cols,
+                 const double* __restrict__ w, double* __restrict__ out) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cols;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        const double* col = x + c;
+        double* o = out + c;
+        if (MODE == SCAN_DIFF) {
+            double prev = col[0];
+            int64_t r = 1;
+            for (; r + 8 <= rows; r += 8) {
+                double v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = col[(r + k) * cols];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    double d = __dsub_rn(v[k], prev);
+                    if (w) d = __ddiv_rn(d, w[r + k - 1]);
+                    o[(r + k - 1) * cols] = d;
+                    prev = v[k];
+                }
+            }
+            for (; r < rows; ++r) {
+                double v = col[r * cols];
+                double d = __dsub_rn(v, prev);
+                if (w) d = __ddiv_rn(d, w[r - 1]);
+                o[(r - 1) * cols] = d;
+                prev = v;
+            }
+        } else {
+            double acc = 0.0;
+            int64_t r = 0;
+            if (MODE == SCAN_CUMSUM) { acc = col[0]; o[0] = acc; r = 1; }
+            else { o[0] = 0.0; }
+            // SCAN_INT consumes x[r] to produce out[r+1]
+            const int64_t last = MODE == SCAN_INT ? rows - 1 : rows;
+            for (; r + 8 <= last; r += 8) {
+                double v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = col[(r + k) * cols];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (MODE == SCAN_INT) {
+                        acc = __dadd_rn(acc, __dmul_rn(v[k], w[r + k]));
+                        o[(r + k + 1) * cols] = acc;
+                    } else {
+                        acc = __dadd_rn(acc, v[k]);
+                        o[(r + k) * cols] = acc;
+                    }
+                }
+            }
+            for (; r < last; ++r) {
+                double v = col[r * cols];
+                if (MODE == SCAN_INT) {
+                    acc = __dadd_rn(acc, __dmul_rn(v, w[r]));
+                    o[(r + 1) * cols] = acc;
+                } else {
+                    acc = __dadd_rn(acc, v);
+                    o[r * cols] = acc;
+                }
+            }
+        }
+    }
+}
+
+extern "C" int sdeb_time_scan(const double* x, int64_t rows, int64_t cols, int64_t mode,
+                              const double* weights, double* out, void* stream_) {
+    if (!x || !out || rows < 1 || cols < 1 || mode < SCAN_CUMSUM || mode > SCAN_DIFF)
+        return fail(SDEB_EINVAL, "sdeb_time_scan: bad arguments");
+    if (mode == SCAN_INT && rows > 1 && !weights)
+        return fail(SDEB_EINVAL, "sdeb_time_scan: SCAN_INT needs the interval weights");
+    if (mode == SCAN_DIFF && rows < 2) return SDEB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int64_t need = (cols + 255) / 256;
+    int blocks = (int)(need < 2368 ? need : 2368);
+    if (mode == SCAN_CUMSUM)
+        time_scan_kernel<SCAN_CUMSUM><<<blocks, 256, 0, stream>>>(x, rows, cols, weights, out);
+    else if (mode == SCAN_INT)
+        time_scan_kernel<SCAN_INT><<<blocks, 256, 0, stream>>>(x, rows, cols, weights, out);
+    else
+        time_scan_kernel<SCAN_DIFF><<<blocks, 256, 0, stream>>>(x, rows, cols, weights, out);
+    CUDA_TRY(cudaGetLastError());
+    return SDEB_OK;
+}
+
+// ---------------------------------------------------------------------------
 // histogram with numpy.histogram bin semantics
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

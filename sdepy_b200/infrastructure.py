@@ -316,6 +316,86 @@ class process(np.ndarray):
     def pmax(self):
         return self._summary('max')
 
+    # ---- timeline helpers, summaries across values and along time ---------
+    # (reference infrastructure.py:731-766, 894-1122)
+    @property
+    def tx(self):
+        return self.t.reshape(self.t.shape + (1,)*(self.ndim - 1))
+
+    @property
+    def dt(self):
+        return np.diff(self.t)
+
+    @property
+    def dtx(self):
+        dt = self.dt
+        return dt.reshape(dt.shape + (1,)*(self.ndim - 1))
+
+    def _vsummary(self, name, **kw):
+        axes = tuple(range(1, self.ndim - 1))
+        return process(t=self.t, x=getattr(np.asarray(self), name)(axis=axes, **kw))
+
+    def _tsummary(self, name, **kw):
+        return process(t=self.t[:1],
+                       x=getattr(np.asarray(self), name)(axis=0, keepdims=True, **kw))
+
+    def vmin(self):
+        return self._vsummary('min')
+
+    def vmax(self):
+        return self._vsummary('max')
+
+    def vsum(self):
+        return self._vsummary('sum')
+
+    def vmean(self):
+        return self._vsummary('mean')
+
+    def vvar(self, ddof=0):
+        return self._vsummary('var', ddof=ddof)
+
+    def vstd(self, ddof=0):
+        return self._vsummary('std', ddof=ddof)
+
+    def tmin(self):
+        return self._tsummary('min')
+
+    def tmax(self):
+        return self._tsummary('max')
+
+    def tsum(self):
+        return self._tsummary('sum')
+
+    def tmean(self):
+        return self._tsummary('mean')
+
+    def tvar(self, ddof=0):
+        return self._tsummary('var', ddof=ddof)
+
+    def tstd(self, ddof=0):
+        return self._tsummary('std', ddof=ddof)
+
+    def tcumsum(self):
+        return process(t=self.t, x=np.asarray(self).cumsum(axis=0))
+
+    def tdiff(self, dt_exp=0, fwd=True):
+        """``q[i] = (p[i+1] - p[i])/(t[i+1] - t[i])**dt_exp`` at ``t[i]``
+        (forward) or ``t[i+1]`` (reference 1032-1080)."""
+        x = np.diff(np.asarray(self), axis=0)
+        if dt_exp:
+            x = x/self.dtx**dt_exp
+        return process(t=self.t[:-1] if fwd else self.t[1:], x=x)
+
+    def tder(self):
+        return self.tdiff(dt_exp=1)
+
+    def tint(self):
+        """Running integral of the piecewise-constant (left value) process
+        (reference 1101-1122)."""
+        x = np.zeros(self.shape)
+        x[1:] = np.asarray(self)[:-1]*self.dtx
+        return process(t=self.t, x=x.cumsum(axis=0))
+
 
 class device_process:
     """A process resident in HBM: ``x`` is a CUDA float64 tensor shaped
@@ -496,6 +576,99 @@ class device_process:
 
     def pmax(self):
         return self._wrap(self._moments()[:, 5])
+
+    # ---- summaries across values and along time, on the slab ---------------
+    # (reference infrastructure.py:894-1122): results stay in HBM as
+    # device_process objects -- path-dependent payoffs (running maximum,
+    # time average, realised variance) never leave the device.
+    def _axis_reduce(self, outer, n_reduce, cols, what, ddof=0):
+        x = self.x if self.x.is_contiguous() else self.x.contiguous()
+        dev = x.device
+        outs = {k: None for k in ('min', 'max', 'sum', 'ssd')}
+        key = {'mean': 'sum', 'var': 'ssd', 'std': 'ssd'}.get(what, what)
+        outs[key] = _cuda.empty((outer*cols,), dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.sdeb_axis_reduce(
+                _cuda.ptr(x), outer, n_reduce, cols,
+                *(None if outs[k] is None else _cuda.ptr(outs[k])
+                  for k in ('min', 'max', 'sum', 'ssd')),
+                float(n_reduce if what == 'mean' else 1), float(n_reduce - ddof),
+                int(what == 'std'), _cuda.stream_ptr(dev)))
+        return outs[key]
+
+    def _tsummary(self, what, ddof=0):
+        n, cols = self.x.shape[0], int(np.prod(self.shape[1:], dtype=int))
+        r = self._axis_reduce(1, n, cols, what, ddof)
+        return device_process(self.t[:1], r.reshape((1,) + self.shape[1:]))
+
+    def _vsummary(self, what, ddof=0):
+        n, V = self.x.shape[0], int(np.prod(self.vshape, dtype=int))
+        r = self._axis_reduce(n, V, self.paths, what, ddof)
+        return device_process(self.t, r.reshape((n, self.paths)))
+
+    def tmin(self):
+        return self._tsummary('min')
+
+    def tmax(self):
+        return self._tsummary('max')
+
+    def tsum(self):
+        return self._tsummary('sum')
+
+    def tmean(self):
+        return self._tsummary('mean')
+
+    def tvar(self, ddof=0):
+        return self._tsummary('var', ddof)
+
+    def tstd(self, ddof=0):
+        return self._tsummary('std', ddof)
+
+    def vmin(self):
+        return self._vsummary('min')
+
+    def vmax(self):
+        return self._vsummary('max')
+
+    def vsum(self):
+        return self._vsummary('sum')
+
+    def vmean(self):
+        return self._vsummary('mean')
+
+    def vvar(self, ddof=0):
+        return self._vsummary('var', ddof)
+
+    def vstd(self, ddof=0):
+        return self._vsummary('std', ddof)
+
+    def _scan(self, mode, weights, rows_out):
+        x = self.x if self.x.is_contiguous() else self.x.contiguous()
+        dev = x.device
+        n, cols = x.shape[0], int(np.prod(self.shape[1:], dtype=int))
+        out = _cuda.empty((rows_out,) + self.shape[1:], dev)
+        w = None if weights is None else _cuda.to_device(
+            np.ascontiguousarray(weights, dtype=float), dev)
+        if rows_out:
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib.sdeb_time_scan(
+                    _cuda.ptr(x), n, cols, mode, None if w is None else _cuda.ptr(w),
+                    _cuda.ptr(out), _cuda.stream_ptr(dev)))
+        return out
+
+    def tcumsum(self):
+        return device_process(self.t, self._scan(_lib.SCAN_CUMSUM, None, len(self)))
+
+    def tdiff(self, dt_exp=0, fwd=True):
+        w = np.diff(self.t)**dt_exp if dt_exp else None
+        return device_process(self.t[:-1] if fwd else self.t[1:],
+                              self._scan(_lib.SCAN_DIFF, w, len(self) - 1))
+
+    def tder(self):
+        return self.tdiff(dt_exp=1)
+
+    def tint(self):
+        return device_process(self.t, self._scan(_lib.SCAN_INT, np.diff(self.t), len(self)))
 
 
 # --------------------------------------------------------------------------

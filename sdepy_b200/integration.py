@@ -606,7 +606,7 @@ class SDE(_jit._traced):
         if cached is not None and cached[0] == key:
             w0l, w0_arg, records = cached[1]
         else:
-            w0 = self._initial_state(tt[self.i0])
+            w0 = self._to_lanes(self._initial_state(tt[self.i0]))
             npaths0 = w0.shape[-1]
             w0l = w0.reshape((spec.groups, spec.nw, npaths0))
             w0_arg = w0l if npaths0 > 1 else w0l[..., 0]
@@ -614,7 +614,7 @@ class SDE(_jit._traced):
                        for seg in segs]
             self._lowered = (key, (w0l, w0_arg, records))
         if replay is not None:
-            replay = [{k: (v.reshape((seg.n_steps, -1, self.paths)))
+            replay = [{k: self._to_lanes(v, 1).reshape((seg.n_steps, -1, self.paths))
                        for k, v in tab.items()} for tab, seg in zip(replay, segs)]
         want_stats = self.output == 'stats'
         centre = self._stats_centre(w0l) if want_stats else None
@@ -644,13 +644,23 @@ class SDE(_jit._traced):
         xshape = self.xshape
         if want_stats:
             torch.cuda.current_stream(res.stats.device).synchronize()
-            sums = res.stats.cpu().numpy().reshape((tt.size,) + xshape + (_lib.NSTAT,))
-            return path_stats(tt, sums, np.asarray(centre).reshape(xshape),
-                              self.paths, self.info)
-        xx = res.out.reshape((tt.size,) + xshape + (self.paths,))
+            sums = self._from_lanes(res.stats.cpu().numpy().reshape(
+                (tt.size, -1, _lib.NSTAT)), (_lib.NSTAT,))
+            centre = self._from_lanes(np.asarray(centre).reshape((1, -1)), ())[0]
+            return path_stats(tt, sums, centre, self.paths, self.info)
+        xx = self._from_lanes(res.out.reshape((tt.size, -1, self.paths)),
+                              (self.paths,))
         if self.output == 'process':
             xx = xx.cpu().numpy()
         return xx
+
+    # layout hooks: the kernel wants the components of one lane adjacent
+    # (element-major); SDEs with addaxis=False store them variable-major
+    def _to_lanes(self, a, pre=0):
+        return a
+
+    def _from_lanes(self, a, tail):
+        return a.reshape(a.shape[:1] + self.xshape + tail)
 
     def _lowering_key(self, tt, grid, replay):
         def ident(z):
@@ -752,13 +762,33 @@ class SDEs(SDE):
 
     def _lanes(self):
         """Traced systems: one lane owns the q variables of an element of
-        vshape (the stacked last axis when addaxis=True, forced for
-        vshape=())."""
+        vshape.  With addaxis=True they are adjacent in the working array;
+        with addaxis=False variable k of element h sits at k*d + h along the
+        last axis (reference 1735-1757) and ``_to_lanes`` / ``_from_lanes``
+        transpose between the two layouts on the way in and out."""
         if not self.addaxis:
-            raise NotImplementedError(
-                'traced systems of SDEs need addaxis=True (or vshape=()): one '
-                'lane owns the q variables of an element of vshape')
-        return self.wshape[:-1], self.q
+            dw = self.sources.get('dw')
+            if isinstance(dw, wiener_source) and dw.corr is not None:
+                raise NotImplementedError(
+                    'a Wiener source correlated across the stacked axis of a '
+                    'traced system needs addaxis=True (one correlation matrix '
+                    'per element of vshape)')
+        return self.vshape, self.q
+
+    def _to_lanes(self, a, pre=0):
+        if self.addaxis:
+            return a
+        v, q = self.vshape, self.q
+        a = a.reshape(a.shape[:pre] + v[:-1] + (q, v[-1]) + a.shape[pre + len(v):])
+        ax = pre + len(v) - 1
+        return a.swapaxes(ax, ax + 1)
+
+    def _from_lanes(self, a, tail):
+        if self.addaxis:
+            return super()._from_lanes(a, tail)
+        v, q = self.vshape, self.q
+        a = a.reshape(a.shape[:1] + v + (q,) + tail)
+        return a.swapaxes(len(v), len(v) + 1).reshape(a.shape[:1] + self.xshape + tail)
 
 
 # --------------------------------------------------------------------------

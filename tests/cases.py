@@ -24,6 +24,11 @@ def hw_corr(t):
     return np.array(((1, c01, c02), (c01, 1, c12), (c02, c12, 1)))
 
 
+def user_system(t, x, y, mu=0., sigma=1., xi=1.):
+    """Same equations as tests/golden/make_golden.py:user_system."""
+    return ({'dt': mu*x, 'dw': y*x}, {'dt': sigma*(1. - y), 'dw': xi*y})
+
+
 HW = dict(factors=3, x0=((.01,), (0.,), (0.,)), theta=hw_theta,
           k=((.1,), (.5,), (1.,)), sigma=((.01,), (.008,), (.005,)),
           corr=hw_corr)

@@ -266,5 +266,57 @@ def main():
          dW=np.diff(np.asarray(dw(t)), axis=0))
 
 
+def user_system(t, x, y, mu=0., sigma=1., xi=1.):
+    """The system of the reference's SDEs docstring (integration.py:1600-1625)
+    with a mean-reverting second equation."""
+    return ({'dt': mu*x, 'dw': y*x}, {'dt': sigma*(1. - y), 'dw': xi*y})
+
+
+def user_system_cases():
+    """User-defined systems through ``integrate(q=2)``, both stacking layouts
+    (addaxis False / True, integration.py:1630-1645)."""
+    for name, addaxis in (('replay_system_stacked', False),
+                          ('replay_system_addaxis', True)):
+        cls = sdepy.integrate(q=2, sources={'dt', 'dw'}, addaxis=addaxis)(user_system)
+        kw = dict(paths=53, vshape=(2, 3), steps=17, x0=(1., .3), mu=.05,
+                  sigma=np.array(((.5,), (1.5,), (1.,))),
+                  xi=np.array((((.2,),), ((.4,),))))
+        probe = cls(rng=np.random.default_rng(5), **kw)
+        rec = recorder(probe.sources['dw'])
+        P = cls(dw=rec, **kw)
+        tt = np.array((0., .25, 1.))
+        x, y = P(tt)
+        save(name, tt=tt, grid=grid_of(P, tt), dW=np.stack(rec.dz),
+             out0=np.asarray(x), out1=np.asarray(y),
+             p_sigma=kw['sigma'], p_xi=kw['xi'])
+
+
+def time_axis_case():
+    """process summaries across values and along the timeline
+    (infrastructure.py:894-1122) on an irregular timeline."""
+    rng = np.random.default_rng(33)
+    t = np.cumsum(rng.uniform(.01, .3, size=19))
+    x = rng.normal(size=(19, 2, 3, 23))*3 + 1
+    p = sdepy.process(t=t, x=x)
+    out = dict(t=t, x=x)
+    for k in ('tmin', 'tmax', 'tsum', 'tmean', 'tvar', 'tstd', 'tcumsum',
+              'tder', 'tint', 'tdiff', 'vmin', 'vmax', 'vsum', 'vmean', 'vvar',
+              'vstd'):
+        out[k] = np.asarray(getattr(p, k)())
+    out['tvar1'] = np.asarray(p.tvar(ddof=1))
+    out['vstd1'] = np.asarray(p.vstd(ddof=1))
+    out['tdiff_half_bwd'] = np.asarray(p.tdiff(dt_exp=.5, fwd=False))
+    out['tdiff_half_bwd_t'] = p.tdiff(dt_exp=.5, fwd=False).t
+    out['tmin_t'] = p.tmin().t
+    save('stats_time_axis', **out)
+
+
 if __name__ == '__main__':
-    main()
+    if sys.argv[1:] == ['systems']:
+        user_system_cases()
+    elif sys.argv[1:] == ['timeaxis']:
+        time_axis_case()
+    else:
+        main()
+        user_system_cases()
+        time_axis_case()

@@ -91,6 +91,41 @@ def test_traced_system_matches_heston_golden():
     assert np.abs(np.exp(np.asarray(a))/g['out0'] - 1).max() <= ULP4
 
 
+@pytest.mark.parametrize('name,addaxis', [('replay_system_stacked', False),
+                                          ('replay_system_addaxis', True)])
+@pytest.mark.parametrize('output', ['process', 'device'])
+def test_user_system_both_stackings_bit_exact(name, addaxis, output):
+    """q=2 system over vshape (2, 3) with per-element parameters, equations
+    stacked along the last vshape axis (the reference's default) or on a new
+    axis: the reference's own output, bit for bit."""
+    from tests.cases import user_system
+    m = sd()
+    g = golden(name)
+    cls = m.integrate(q=2, sources={'dt', 'dw'}, addaxis=addaxis)(user_system)
+    P = cls(paths=g['dW'].shape[-1], vshape=(2, 3), steps=g['grid'],
+            x0=(1., .3), mu=.05, sigma=g['p_sigma'], xi=g['p_xi'],
+            dw=m.replay_source(g['dW']), output=output)
+    x, y = P(g['tt'])
+    if output == 'device':
+        x, y = x.x.cpu().numpy(), y.x.cpu().numpy()
+    assert np.array_equal(np.asarray(x), g['out0'])
+    assert np.array_equal(np.asarray(y), g['out1'])
+
+
+def test_user_system_stacked_statistics():
+    """output='stats' of a variable-major system: same entries as the paths."""
+    from tests.cases import user_system
+    m = sd()
+    g = golden('replay_system_stacked')
+    cls = m.integrate(q=2, sources={'dt', 'dw'})(user_system)
+    kw = dict(paths=g['dW'].shape[-1], vshape=(2, 3), steps=g['grid'],
+              x0=(1., .3), mu=.05, sigma=g['p_sigma'], xi=g['p_xi'])
+    st = cls(dw=m.replay_source(g['dW']), output='stats', **kw)(g['tt'])
+    ref = np.concatenate((g['out0'], g['out1']), axis=-2)
+    assert np.allclose(np.asarray(st.pmean())[..., 0], ref.mean(axis=-1), rtol=1e-13)
+    assert np.array_equal(np.asarray(st.pmax())[..., 0], ref.max(axis=-1))
+
+
 def test_milstein_replay_matches_oracle_and_beats_euler():
     m = sd()
     rng = np.random.default_rng(2)

@@ -107,3 +107,19 @@ def test_black_scholes_call_put_within_3_stderr():
             price = float(np.asarray(st.payoff_mean())[-1, 0])
             err = float(np.asarray(st.payoff_stderr())[-1, 0])
             assert abs(price - want) < 3.5*err, (T, kind, price, want, err)
+
+
+def test_kfunc_shortcuts_evaluate_on_the_device():
+    """``sdepy.lognorm(...)(timeline, paths=..., steps=...)`` and the one-shot
+    ``sdepy.dw(t, dt, paths=...)`` forms (reference shortcuts.py:73-99)."""
+    import sdepy_b200 as m
+    tt = np.linspace(0., 1., 5)
+    P = m.lognorm(x0=1., mu=.05, sigma=.2, seed=3)
+    x = P(tt, paths=20000, steps=50)
+    assert isinstance(x, m.process) and x.shape == (5, 20000)
+    assert abs(float(x[-1].mean()) - np.exp(.05)) < 4*.2123744/np.sqrt(20000)
+    z = m.dw(0., .25, paths=50000, seed=4)
+    assert tuple(z.shape) == (50000,)
+    assert abs(float(z.std()) - .5) < .01
+    xy = m.heston_xy(tt, paths=1000, steps=20, seed=5)
+    assert len(xy) == 2 and xy[0].shape == (5, 1000)

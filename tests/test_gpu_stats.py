@@ -127,3 +127,47 @@ def test_cdf_chf_of_a_simulated_process_against_closed_forms():
     f = x.chf(t[[0, 2]], uq)
     wantf = np.exp(-uq[None, :]**2*t[[0, 2], None]/2)
     assert np.abs(f - wantf).max() < 5/np.sqrt(paths)
+
+
+def test_device_process_time_and_value_summaries_bit_exact():
+    """tmin .. tint and vmin .. vstd on the resident slab: the reference's own
+    results (sequential NumPy reductions of a non-contiguous axis), bit for
+    bit, and the results stay on the device."""
+    from tests.test_oracle_golden import TIME_AXIS
+    m = sd()
+    g = golden('stats_time_axis')
+    dp = m.device_process(g['t'], torch.from_numpy(g['x']).cuda())
+    for k in TIME_AXIS:
+        r = getattr(dp, k)()
+        assert isinstance(r, m.device_process) and r.x.is_cuda, k
+        assert r.shape == g[k].shape, (k, r.shape, g[k].shape)
+        assert np.array_equal(r.x.cpu().numpy(), g[k]), k
+    assert np.array_equal(dp.tvar(ddof=1).x.cpu().numpy(), g['tvar1'])
+    assert np.array_equal(dp.vstd(ddof=1).x.cpu().numpy(), g['vstd1'])
+    q = dp.tdiff(dt_exp=.5, fwd=False)
+    assert np.array_equal(q.x.cpu().numpy(), g['tdiff_half_bwd'])
+    assert np.array_equal(q.t, g['tdiff_half_bwd_t'])
+    assert np.array_equal(dp.tmin().t, g['tmin_t'])
+    # NaNs propagate through min / max like NumPy's
+    x = g['x'].copy()
+    x[5, 1, 2, 7] = np.nan
+    dn = m.device_process(g['t'], torch.from_numpy(x).cuda())
+    assert np.array_equal(dn.tmax().x.cpu().numpy(), x.max(axis=0, keepdims=True),
+                          equal_nan=True)
+
+
+def test_path_dependent_payoffs_on_the_device():
+    """Asian and lookback payoffs of a simulated lognormal process computed
+    from the resident slab (doc/quickguide.rst:663-669 does this on the host):
+    same numbers as NumPy on the copied-back paths."""
+    m = sd()
+    tt = np.linspace(0., 1., 53)
+    p = m.lognorm_process(x0=100., mu=.03, sigma=.2, paths=20000, steps=tt,
+                          seed=9, output='device')(tt)
+    host = p.cpu()
+    asian = np.maximum(np.asarray(host).mean(axis=0) - 100., 0.)
+    lookback = np.asarray(host).max(axis=0) - np.asarray(host)[-1]
+    a = (p.tmean().x[0] - 100.).clamp_min(0.)
+    lb = p.tmax().x[0] - p.x[-1]
+    assert np.array_equal(a.cpu().numpy(), asian)
+    assert np.array_equal(lb.cpu().numpy(), lookback)

@@ -234,3 +234,69 @@ def test_host_process_cdf_chf_interp_match_reference():
     assert np.allclose(p.chf(g['tq'], g['uq']), g['chf_t'], rtol=1e-14, atol=1e-16)
     with pytest.raises(TypeError):
         p.cdf()
+
+
+def test_stacked_system_lane_layout_round_trip():
+    """SDEs with addaxis=False keep variable k of element h at k*d + h along
+    the last axis (reference integration.py:1735-1757); the kernel wants the q
+    variables of an element adjacent.  _to_lanes / _from_lanes transpose
+    between the two and are inverse to each other."""
+    import sdepy_b200 as m
+    from tests.cases import user_system
+    cls = m.integrate(q=2, sources={'dt', 'dw'})(user_system)
+    P = cls(paths=5, vshape=(2, 3), steps=4, x0=(1., .3))
+    assert P.wshape == (2, 6) and P._lanes() == ((2, 3), 2)
+    w = np.arange(2*6*5, dtype=float).reshape(2, 6, 5)
+    lanes = P._to_lanes(w)                       # (2, 3, q, paths)
+    assert lanes.shape == (2, 3, 2, 5)
+    x, y = P.unpack(w)
+    assert np.array_equal(lanes[..., 0, :], x) and np.array_equal(lanes[..., 1, :], y)
+    rows = np.stack((w, 2*w))
+    flat = P._to_lanes(rows, 1).reshape(2, -1, 5)
+    assert np.array_equal(P._from_lanes(flat, (5,)), rows)
+    # addaxis=True: identity
+    Q = m.integrate(q=2, sources={'dt', 'dw'}, addaxis=True)(user_system)(
+        paths=5, vshape=(2, 3), steps=4, x0=(1., .3))
+    w = np.zeros((2, 3, 2, 5))
+    assert Q._to_lanes(w) is w and Q._lanes() == ((2, 3), 2)
+
+
+def test_kfunc_parameter_management():
+    """The documented kfunc protocol (reference kfun.py:262-341): parameters
+    stored, variables given at evaluation, re-instantiation on new parameters."""
+    import sdepy_b200 as m
+
+    class scaled:
+        def __init__(self, *, a=1., b=0.):
+            self.a, self.b = a, b
+
+        def __call__(self, t, dt=1.):
+            return self.a*t + self.b*dt
+
+    K = m.kfunc(scaled)
+    assert m.iskfunc(K) and not m.iskfunc(scaled) and m.kfunc(K) is K
+    inst = K(a=2.)
+    assert m.iskfunc(inst) and isinstance(inst, scaled)
+    assert inst.params == {'a': 2., 'b': 0.}
+    assert inst(3.) == 6. and inst(t=3., dt=2.) == 6.
+    assert inst(3., b=1.) == 7. and inst.b == 0.          # inst unaffected
+    other = inst(b=5.)
+    assert other.params == {'a': 2., 'b': 5.} and other is not inst
+    assert K(3., 2., a=1., b=1.) == 5.                     # instantiate + evaluate
+    assert K(a=1., b=1., dt=2., t=3.) == 5.                # variables by name
+
+    @m.kfunc(nvar=1)
+    def line(t, a=1., b=2.):
+        return a*t + b
+    g = line(a=3.)
+    assert g(2.) == 8. and g(2., b=0.) == 6. and line(2., a=1.) == 4.
+    assert g(b=5.).params == {'a': 3., 'b': 5.}
+    with pytest.raises(TypeError):
+        line(c=1.)
+
+    # the shortcuts are kfuncs over the plain classes, which stay plain
+    assert m.iskfunc(m.lognorm) and not m.iskfunc(m.lognorm_process)
+    P = m.heston(x0=100., rho=-.7, paths=10)
+    Q = P(paths=20, steps=7)
+    assert (P.paths, Q.paths, Q.params['steps']) == (10, 20, 7)
+    assert isinstance(Q, m.heston_process) and Q.params['rho'] == -.7

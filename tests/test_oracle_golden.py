@@ -32,6 +32,19 @@ def test_replay_bit_exact(name):
     assert int(g['stored_steps']) == g['tt'].size - 1
 
 
+@pytest.mark.parametrize('name,addaxis', [('replay_system_stacked', False),
+                                          ('replay_system_addaxis', True)])
+def test_user_system_replay_bit_exact(name, addaxis):
+    """Both stacking layouts of a user-defined q=2 system."""
+    from tests.cases import user_system
+    g = golden(name)
+    where = np.searchsorted(g['grid'], g['tt'])
+    x, y = orc.system_replay(
+        user_system, 2, dict(mu=.05, sigma=g['p_sigma'], xi=g['p_xi']),
+        (1., .3), g['grid'], where, g['dW'], addaxis)
+    assert np.array_equal(x, g['out0']) and np.array_equal(y, g['out1'])
+
+
 def test_step_grid_matches_reference_merge():
     for name in sorted(REPLAY):
         g = golden(name)
@@ -127,3 +140,24 @@ def test_known_answer_lognorm_exact():
     exact = np.exp((.05 - .2*.2/2)*t[:, None] + .2*g['w'])
     assert np.allclose(out, exact, rtol=16*np.finfo(float).resolution)
     assert np.allclose(out, g['x'], rtol=1e-13)
+
+
+TIME_AXIS = ('tmin', 'tmax', 'tsum', 'tmean', 'tvar', 'tstd', 'tcumsum', 'tder',
+             'tint', 'tdiff', 'vmin', 'vmax', 'vsum', 'vmean', 'vvar', 'vstd')
+
+
+def test_host_process_time_and_value_summaries_match_reference():
+    """The host container's t* / v* methods (reference infrastructure.py:
+    894-1122), bit for bit against the reference's own results."""
+    import sdepy_b200 as m
+    g = golden('stats_time_axis')
+    p = m.process(t=g['t'], x=g['x'])
+    for k in TIME_AXIS:
+        r = getattr(p, k)()
+        assert np.array_equal(np.asarray(r), g[k]), k
+    assert np.array_equal(np.asarray(p.tvar(ddof=1)), g['tvar1'])
+    assert np.array_equal(np.asarray(p.vstd(ddof=1)), g['vstd1'])
+    q = p.tdiff(dt_exp=.5, fwd=False)
+    assert np.array_equal(np.asarray(q), g['tdiff_half_bwd'])
+    assert np.array_equal(q.t, g['tdiff_half_bwd_t'])
+    assert np.array_equal(p.tmin().t, g['tmin_t'])
