@@ -458,7 +458,7 @@ class _traced:
         tdep = tdep or any(callable(z) for z in
                            self._get_args(self._sde_args_keys).values())
         corr_t = not replay and isinstance(dw, wiener_source) and callable(dw.corr)
-        jumps_t = spec.jumps and not replay
+        jumps_t = spec.jumps and not replay and self._jumps_time_dependent()
         n = seg.n_steps if (tdep or corr_t or jumps_t) and seg.n_steps else 1
         ncomp = self._rec_comps
         blocks = []
@@ -480,8 +480,7 @@ class _traced:
                         lam_src = dj.dn
                         kind, a, b, pa = dj.y.at(mid)
                     lam = lane_values(lam_src.lam_at(mid), lanes, 'lam', paths=self.paths)
-                    lamdt = np.abs(ds)*lam
-                    cols += [lamdt, np.exp(-lamdt), zero + kind] + [
+                    cols += [lam, zero, zero + kind] + [
                         lane_values(z, lanes, 'jump law parameter', paths=self.paths)
                         for z in (a, b, pa)]
             block = (stack_lane_columns(cols, spec.groups, ncomp) if cols

@@ -581,6 +581,15 @@ class SDE(_jit._traced):
                 'implementation')
         return self.sources.get('dj', self.sources.get('dn'))
 
+    def _jumps_time_dependent(self):
+        """True when the jump intensity or the jump-size law change in time
+        (both are sampled at step midpoints, infrastructure.py:1630, 2031)."""
+        dj = self._jump_source()
+        lam_src = getattr(dj, 'dn', dj)
+        law = getattr(dj, 'y', None)
+        return callable(getattr(lam_src, 'lam', None)) or any(
+            callable(z) for z in getattr(law, 'params', {}).values())
+
     def _philox_key(self):
         for id in ('dw', 'dj', 'dn'):
             src = self.sources.get(id)
@@ -855,6 +864,11 @@ class _preset_SDE(SDE):
             return self.wshape[:-1], self.wshape[-1]
         return super()._lanes()
 
+    # the hand-written functors address the reference's own working layout
+    # (Heston: N x-components then N y-components, integration.py:2460-2466)
+    _to_lanes = SDE._to_lanes
+    _from_lanes = SDE._from_lanes
+
     def _spec(self):
         lead, ncomp = self._lanes()
         groups = int(np.prod(lead, dtype=int))
@@ -878,7 +892,7 @@ class _preset_SDE(SDE):
         dj = self.sources.get('dj')
         tdep = any(callable(z) for z in sde_args.values())
         corr_t = (not replay and isinstance(dw, wiener_source) and callable(dw.corr))
-        jumps_t = spec.jumps and not replay
+        jumps_t = spec.jumps and not replay and self._jumps_time_dependent()
         n = seg.n_steps if (tdep or corr_t or jumps_t) else 1
         n = max(n, 1) if seg.n_steps else 1
         ncomp = spec.ncomp
@@ -914,9 +928,10 @@ class _preset_SDE(SDE):
             return [zero]*6
         mid = s + ds/2
         lam = self._lane_matrix(dj.dn.lam_at(mid), full)     # midpoint, 1630
-        lamdt = np.abs(ds)*lam
         kind, a, b, pa = dj.y.at(mid)                        # midpoint, 2031
-        return [lamdt, np.exp(-lamdt), zero + kind,
+        # the kernel forms |dt|*lam itself: the record is constant in time
+        # unless lam or the jump law are
+        return [lam, zero, zero + kind,
                 self._lane_matrix(a, full), self._lane_matrix(b, full),
                 self._lane_matrix(pa, full)]
 

@@ -254,6 +254,10 @@ def test_stacked_system_lane_layout_round_trip():
     rows = np.stack((w, 2*w))
     flat = P._to_lanes(rows, 1).reshape(2, -1, 5)
     assert np.array_equal(P._from_lanes(flat, (5,)), rows)
+    # presets address the reference's working layout natively
+    H = m.full_heston_process(paths=5, vshape=(2,), steps=4)
+    w4 = np.zeros((4, 5))
+    assert H._to_lanes(w4) is w4 and H._lanes() == ((), 2)
     # addaxis=True: identity
     Q = m.integrate(q=2, sources={'dt', 'dw'}, addaxis=True)(user_system)(
         paths=5, vshape=(2, 3), steps=4, x0=(1., .3))

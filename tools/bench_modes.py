@@ -138,6 +138,29 @@ def main():
         x0=1., mu=.05, sigma=.2, lam=2., a=.1, b=.15, pa=.4, paths=p, steps=n + 1, seed=6,
         output='stats', getinfo=False)((0., 1.)))
     rec('C4 kou terminal stats (philox)', p, n, t)
+    t, x = timed(lambda: sd.merton_jumpdiff_process(
+        x0=1., mu=.05, sigma=.2, lam=2., a=-.1, b=.15, paths=p, steps=n + 1, seed=5,
+        output='stats')((0., 1.)))
+    rec('C4 merton terminal stats (philox, getinfo: jump_count + jump_rate)', p, n, t)
+    # summaries of a resident slab along the timeline (path-dependent payoffs)
+    p, n = int(1_000_000*a.scale), 500
+    proc = sd.ornstein_uhlenbeck_process(x0=.1, theta=.2, k=1., sigma=.3, paths=p, seed=8,
+                                         output='device')(np.linspace(0., 5., n + 1))
+    for name, fn, passes_r, passes_w in (('tmax', proc.tmax, 1, 0), ('tmean', proc.tmean, 1, 0),
+                                         ('tstd', proc.tstd, 2, 0), ('tcumsum', proc.tcumsum, 1, 1),
+                                         ('tdiff', proc.tdiff, 1, 1), ('tint', proc.tint, 1, 1)):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1)*1e-3)
+            del r
+        nbytes = 8.*(n + 1)*p*(passes_r + passes_w)
+        res.append(dict(config='device_process.%s on (%d, %d)' % (name, n + 1, p),
+                        seconds=min(ts), GBps=nbytes/min(ts)/1e9,
+                        frac_of_copy_peak=nbytes/min(ts)/1e9/HBM_GBS))
+    del proc
     # C5: custom @integrate, Milstein, 1e8 x 2000, montecarlo of the terminal value
     @sd.integrate
     def gbm(t, x, mu=.05, sigma=.2):
