@@ -742,10 +742,11 @@ draw_wiener_kernel(const NrmK nk, double* out, int n_groups, int ndw, int64_t n_
     rng.rk = rk;
     rng.c_x = (u32)gpath; rng.c_y = ((u32)(gpath >> 32) & 0xFFu) | ((u32)g << 8);
     rng.step = step;
-    double z[34];
-    for (int b = 0; b < (ndw + 1) / 2; ++b) {
+    double z[36];
+    for (int b = 0; b < (ndw + 3) / 4; ++b) {      // one block = two pairs
         U4 w = rng.block((u32)b);
-        normal_pair(w, tab, nk, 1.0, z[2*b], z[2*b + 1]);
+        normal_pair(w.x, w.y, tab, nk, 1.0, z[4*b], z[4*b + 1], TailDraw{rng, (u32)(2*b)});
+        normal_pair(w.z, w.w, tab, nk, 1.0, z[4*b + 2], z[4*b + 3], TailDraw{rng, (u32)(2*b + 1)});
     }
     for (int r = ndw - 1; r >= 0; --r) {
         double acc = z[r];
@@ -796,10 +797,11 @@ bridge_wiener_kernel(const NrmK nk, double* out, const double* w1, const double*
     rng.rk = rk;
     rng.c_x = (u32)gpath; rng.c_y = ((u32)(gpath >> 32) & 0xFFu) | ((u32)g << 8);
     rng.step = step;
-    double z[34];
-    for (int b = 0; b < (ndw + 1) / 2; ++b) {
+    double z[36];
+    for (int b = 0; b < (ndw + 3) / 4; ++b) {      // one block = two pairs
         U4 w = rng.block((u32)b);
-        normal_pair(w, tab, nk, 1.0, z[2*b], z[2*b + 1]);
+        normal_pair(w.x, w.y, tab, nk, 1.0, z[4*b], z[4*b + 1], TailDraw{rng, (u32)(2*b)});
+        normal_pair(w.z, w.w, tab, nk, 1.0, z[4*b + 2], z[4*b + 3], TailDraw{rng, (u32)(2*b + 1)});
     }
     const double* M1 = s_m; const double* M2 = s_m + ndw * ndw; const double* Ly = s_m + 2 * ndw * ndw;
     for (int r = 0; r < ndw; ++r) {
@@ -890,16 +892,17 @@ __global__ void test_normals_kernel(const NrmK nk, u64 seed, int64_t n, double* 
     rng.rk = rk;
     rng.c_x = (u32)i; rng.c_y = (u32)(i >> 32); rng.step = 0;
     U4 w = rng.block(0);
-    if (i < 64) {   // force the extreme corners of the bit space through both maps
-        if (i & 1) w.x = 0;             // e = 33: deepest tail
-        if (i & 2) { w.y = 0xFFFFFFFFu; w.z = 0xFFFFFFFFu; }   // m -> 2
-        if (i & 4) { w.y = 0; w.z = 0; }                       // m = 1
-        if (i & 8) w.x = 0x80000000u;   // e = 1
-        if (i & 16) w.w = 0xFFFFFFFFu;
-        if (i & 32) w.w = 0;
+    if (i < 128) {   // force the extreme corners of the bit space through both maps
+        if (i & 1) { w.x &= 0x000FFFFFu; w.z = 0; }            // e = 45: deepest tail
+        if (i & 2) { w.x |= 0x000FFFFFu; w.y |= 0xFF000000u; } // m -> 2
+        if (i & 4) { w.x &= 0xFFF00000u; w.y &= 0x00FFFFFFu; } // m = 1
+        if (i & 8) w.x |= 0x80000000u;  // e = 1
+        if (i & 16) w.y |= 0x00FFFFFFu; // last sector, largest offset
+        if (i & 32) w.y &= 0xFF000000u; // first sector, most negative offset
+        if (i & 64) { w.x &= 0x000FFFFFu; w.z = 0x80000000u; } // e = 13
     }
-    normal_pair(w, tab, nk, 1.0, zf[2*i], zf[2*i + 1]);
-    normal_pair_libdevice(w, zl[2*i], zl[2*i + 1]);
+    normal_pair(w.x, w.y, tab, nk, 1.0, zf[2*i], zf[2*i + 1], TailWord{w.z});
+    normal_pair_libdevice(w.x, w.y, zl[2*i], zl[2*i + 1], TailWord{w.z});
 }
 
 extern "C" int sdeb_test_normals(uint64_t seed, int64_t n, double* z_fast, double* z_libdevice,

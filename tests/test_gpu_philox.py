@@ -31,8 +31,15 @@ def test_normal_pair_matches_libdevice():
     # z = r (cos, sin) -- only visible in the forced corner u -> 1 (r -> 0)
     r = np.maximum(np.hypot(zl[0::2], zl[1::2]), 1e-300).repeat(2)
     assert (np.abs(zf - zl) < 4e-15 + 3e-16/r).all()
-    assert np.abs(zf - zl)[128:].max() < 1e-13
-    z = zf[128:]
+    assert np.abs(zf - zl)[256:].max() < 1e-13
+    z = zf[256:]
+    # radius tail: P(u < 2^-k) = 2^-k on both sides of the 12-bit exponent field
+    # (beyond it the leading-zero count continues in an extra Philox word)
+    r2 = z[0::2]**2 + z[1::2]**2
+    for k in (8, 12, 14, 16):
+        want = r2.size*2.**-k
+        got = (r2 > 2*k*np.log(2.)).sum()
+        assert abs(got - want) < 5*np.sqrt(want), (k, got, want)
     assert abs(z.mean()) < 4/np.sqrt(z.size)
     assert abs(z.var() - 1) < 4*np.sqrt(2/z.size)
     assert abs((z**4).mean() - 3) < 4*np.sqrt(96/z.size)
