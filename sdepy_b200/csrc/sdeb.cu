@@ -729,7 +729,7 @@ extern "C" int sdeb_histogram(const double* x, int64_t n, const double* edges, i
 __global__ void __launch_bounds__(256)
 draw_wiener_kernel(const NrmK nk, double* out, int n_groups, int ndw, int64_t n_paths, int64_t pitch,
                    int64_t path_offset, u64 seed, u32 step, double sq, const double* chol) {
-    __shared__ double tab[TAB_DOUBLES];
+    __shared__ __align__(16) double tab[TAB_DOUBLES];
     fill_tables(tab);
     __syncthreads();
     const int64_t path = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(256)
 bridge_wiener_kernel(const NrmK nk, double* out, const double* w1, const double* w2,
                      const double* mats, int ndw, int64_t n_paths, int64_t pitch,
                      int64_t path_offset, u64 seed, u32 step) {
-    __shared__ double tab[TAB_DOUBLES];
+    __shared__ __align__(16) double tab[TAB_DOUBLES];
     __shared__ double s_m[3 * 32 * 32];
     fill_tables(tab);
     for (int i = threadIdx.x; i < 3 * ndw * ndw; i += blockDim.x) s_m[i] = mats[i];
@@ -835,7 +835,7 @@ __global__ void __launch_bounds__(256)
 draw_cpoisson_kernel(const NrmK nk, double* dj, i64* dn, int64_t n_paths, int64_t pitch, int64_t path_offset,
                      u64 seed, u32 step, double lamdt, double explam, int sign, int law,
                      double a, double b, double pa) {
-    __shared__ double tab[TAB_DOUBLES];
+    __shared__ __align__(16) double tab[TAB_DOUBLES];
     fill_tables(tab);
     __syncthreads();
     const int64_t path = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -881,7 +881,7 @@ extern "C" int sdeb_draw_cpoisson(double* dj, int64_t* dn, int64_t n_lanes, int6
 // self tests / measurement
 // ---------------------------------------------------------------------------
 __global__ void test_normals_kernel(const NrmK nk, u64 seed, int64_t n, double* zf, double* zl) {
-    __shared__ double tab[TAB_DOUBLES];
+    __shared__ __align__(16) double tab[TAB_DOUBLES];
     fill_tables(tab);
     __syncthreads();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
