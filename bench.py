@@ -321,7 +321,10 @@ def run_ours(a):
                         'figure). "executed" is the FP64-pipe utilisation of the '
                         'instructions this kernel really issues (%d per path-step: '
                         'its log/sqrt/sincos are hand-rolled), = ncu '
-                        'sm__pipe_fp64_cycles_active'
+                        'sm__pipe_fp64_cycles_active; frac can exceed 1 because '
+                        'the SURVEY figure prices the transcendentals at libdevice '
+                        'cost, which this kernel undercuts -- "executed" is the '
+                        'utilisation to read'
                         % (ALGO_FP64_INSTR_PER_PATH_STEP, N64_PER_PATH_STEP)},
             'check': {'call_price_last_step': pay_mean, 'stderr': pay_se,
                       'closed_form': 9.2425, 'e2e_price': price},
