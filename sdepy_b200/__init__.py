@@ -8,7 +8,7 @@ of the reference's Python surface for that path.  No CPU fallback.
 """
 from . import _lib                                   # fails loudly if the .so is missing
 from .infrastructure import (                        # noqa: F401
-    process, device_process, montecarlo,
+    process, piecewise, device_process, montecarlo,
     source, wiener_source, poisson_source, cpoisson_source, replay_source,
     odd_wiener_source, even_poisson_source, even_cpoisson_source, true_wiener_source,
     norm_rv, uniform_rv, exp_rv, double_exp_rv)

@@ -219,11 +219,79 @@ class process(np.ndarray):
         self.t = t if (t is not None and t.shape == self.shape[:1]) else None
 
     def __array_wrap__(self, out, context=None, return_scalar=False):
-        if context is None or out.shape[:1] != self.shape[:1]:
+        """ufunc results stay processes, on the common non-constant timeline of
+        the process operands (reference infrastructure.py:505-540); ndarray
+        methods (sum, mean ...) return plain arrays."""
+        if context is None:
+            return np.asarray(out)
+        t = None
+        for a in context[1]:
+            ta = getattr(a, 't', None) if isinstance(a, process) else None
+            if ta is not None and ta.shape == out.shape[:1] and (t is None or t.size == 1):
+                t = ta
+        if t is None:
             return np.asarray(out)
         res = np.asarray(out).view(type(self))
-        res.t = self.t
+        res.t = t
         return res
+
+    # ---- process-specific indexing (reference infrastructure.py:653-707) ---
+    def __getitem__(self, key):
+        """Plain ndarray indexing returns plain arrays; ``p['t', i]``,
+        ``p['p', i]`` and ``p['v', i, j ...]`` index the timeline, the paths
+        and the values and return processes (an integer index keeps its axis)."""
+        x = self.view(np.ndarray)
+        if isinstance(key, str):
+            key = (key,)
+        if not (isinstance(key, tuple) and key and isinstance(key[0], str)):
+            return x[key]
+        mode, idx = key[0], key[1:]
+        if len(idx) == 1 and isinstance(idx[0], tuple):
+            idx = idx[0]
+        if mode == 'v':
+            return type(self)(self.t, x=x[(slice(None),) + idx + (slice(None),)])
+        if mode not in ('t', 'p'):
+            raise IndexError('process indexing error - unsupported indexing '
+                             'mode ' + repr(mode))
+        if len(idx) > 1:
+            raise IndexError("process indexing error - one index expected in "
+                             "'t' and 'p' modes")
+        if idx and isinstance(idx[0], (int, np.integer)):
+            i = int(idx[0])
+            idx = (slice(i, None) if i == -1 else slice(i, i + 1),)
+        if mode == 't':
+            return type(self)(self.t[idx], x=x[idx])
+        return type(self)(self.t, x=x[(Ellipsis,) + idx])
+
+    def rebase(self, t, *, kind=None):
+        """Process with timeline ``t`` and interpolated values (635-651)."""
+        t = np.asarray(t)
+        t = t.reshape(1) if t.ndim == 0 else t
+        return process(t, x=self(t, kind=kind))
+
+    def shapeas(self, vshape_or_process):
+        """Add / remove leading 1-axes of the values so as to broadcast against
+        values of the given shape (769-801)."""
+        vshape = (vshape_or_process.vshape if isinstance(vshape_or_process, process)
+                  else _shape_setup(vshape_or_process))
+        k, h = self.ndim - 2, len(vshape)
+        if h >= k:
+            newshape = self.shape[:1] + (1,)*(h - k) + self.shape[1:]
+        else:
+            if set(self.shape[1:k - h + 1]) != {1}:
+                raise ValueError('could not reshape {} process values as {}'
+                                 .format(self.vshape, vshape))
+            newshape = self.shape[:1] + self.shape[k - h + 1:]
+        return type(self)(self.t, x=self.view(np.ndarray).reshape(newshape))
+
+    def pcopy(self, **args):
+        return type(self)(t=self.t.copy(**args), x=self.view(np.ndarray).copy(**args))
+
+    def xcopy(self, **args):
+        return type(self)(t=self.t, x=self.view(np.ndarray).copy(**args))
+
+    def tcopy(self, **args):
+        return type(self)(t=self.t.copy(**args), x=self.view(np.ndarray))
 
     @property
     def x(self):
@@ -395,6 +463,31 @@ class process(np.ndarray):
         x = np.zeros(self.shape)
         x[1:] = np.asarray(self)[:-1]*self.dtx
         return process(t=self.t, x=x.cumsum(axis=0))
+
+
+def piecewise(t=0., *, x=None, v=None, dtype=None, mode='mid'):
+    """Process interpolating to a piecewise constant function: ``t[i]`` is the
+    midpoint ('mid'), start ('forward') or end ('backward') of the segment
+    with value ``x[i]`` (reference infrastructure.py:1216-1281).  Usable as a
+    time-dependent SDE parameter (nearest-neighbour interpolation)."""
+    p = process(t, x=x, v=v, dtype=dtype)
+    t, x = p.t, p.x
+    if mode == 'mid':
+        s, y = t, x
+    elif mode in ('forward', 'backward'):
+        # every knot doubled: the value switches AT the knot
+        s = np.repeat(t, 2)
+        y = np.repeat(x, 2, axis=0)
+        if mode == 'forward':
+            y[2::2] = x[:-1]          # left copy of knot i carries value i-1
+        else:
+            y[1:-1:2] = x[1:]         # right copy of knot i carries value i+1
+    else:
+        raise ValueError("mode should be one of 'mid', 'forward', 'backward', "
+                         'but {} was given'.format(mode))
+    p = process(s, x=y, dtype=dtype)
+    p.interp_kind = 'nearest'
+    return p
 
 
 class device_process:

@@ -311,8 +311,42 @@ def time_axis_case():
     save('stats_time_axis', **out)
 
 
+CONTAINER_KEYS = {
+    't_int': ('t', 2), 't_last': ('t', -1), 't_slice': ('t', slice(1, 4)),
+    'p_int': ('p', 3), 'p_slice': ('p', slice(0, 5, 2)), 'p_list': ('p', [1, 3]),
+    'v_int': ('v', 1), 'v_two': ('v', 1, 2), 'v_tuple': ('v', (0, 1)),
+    'v_mixed': ('v', slice(None), 0)}
+
+
+def process_container_case():
+    """process indexing modes, rebase, shapeas, piecewise and ufunc timeline
+    propagation (infrastructure.py:505-540, 635-707, 769-801, 1216-1281)."""
+    rng = np.random.default_rng(44)
+    t = np.linspace(0, 1, 5)
+    x = rng.normal(size=(5, 2, 3, 7))
+    p = sdepy.process(t, x=x)
+    out = dict(t=t, x=x)
+    for name, key in CONTAINER_KEYS.items():
+        q = p[key]
+        out[name] = np.asarray(q)
+        out[name + '_t'] = q.t
+    q = p.rebase((0.1, .55))
+    out['rebase'], out['rebase_t'] = np.asarray(q), q.t
+    out['shapeas'] = np.asarray(p['v', 0].shapeas((4, 3)))
+    c = sdepy.process(c=(1., 2., 3.))
+    q = c.shapeas(p['v', 0])*p['v', 0]
+    out['const_times'], out['const_times_t'] = np.asarray(q), q.t
+    s = np.linspace(-.2, 1.2, 57)
+    out['s'] = s
+    for mode in ('mid', 'forward', 'backward'):
+        out['piecewise_' + mode] = sdepy.piecewise(t, v=x[..., 0], mode=mode)(s)
+    save('process_container', **out)
+
+
 if __name__ == '__main__':
-    if sys.argv[1:] == ['systems']:
+    if sys.argv[1:] == ['container']:
+        process_container_case()
+    elif sys.argv[1:] == ['systems']:
         user_system_cases()
     elif sys.argv[1:] == ['timeaxis']:
         time_axis_case()
@@ -320,3 +354,4 @@ if __name__ == '__main__':
         main()
         user_system_cases()
         time_axis_case()
+        process_container_case()

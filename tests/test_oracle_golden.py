@@ -161,3 +161,40 @@ def test_host_process_time_and_value_summaries_match_reference():
     assert np.array_equal(np.asarray(q), g['tdiff_half_bwd'])
     assert np.array_equal(q.t, g['tdiff_half_bwd_t'])
     assert np.array_equal(p.tmin().t, g['tmin_t'])
+
+
+def test_host_process_container_matches_reference():
+    """``p['t'|'p'|'v', ...]`` indexing, rebase, shapeas, piecewise and the
+    timeline carried through ufuncs, against the reference's own results."""
+    import sdepy_b200 as m
+    keys = {
+        't_int': ('t', 2), 't_last': ('t', -1), 't_slice': ('t', slice(1, 4)),
+        'p_int': ('p', 3), 'p_slice': ('p', slice(0, 5, 2)), 'p_list': ('p', [1, 3]),
+        'v_int': ('v', 1), 'v_two': ('v', 1, 2), 'v_tuple': ('v', (0, 1)),
+        'v_mixed': ('v', slice(None), 0)}
+    g = golden('process_container')
+    p = m.process(g['t'], x=g['x'])
+    for name, key in keys.items():
+        q = p[key]
+        assert isinstance(q, m.process), name
+        assert np.array_equal(np.asarray(q), g[name]) and np.array_equal(q.t, g[name + '_t']), name
+    assert not isinstance(p[2], m.process) and np.array_equal(p[1:3, 0], g['x'][1:3, 0])
+    with pytest.raises(IndexError):
+        p['w', 0]
+    q = p.rebase((0.1, .55))
+    assert np.array_equal(np.asarray(q), g['rebase']) and np.array_equal(q.t, g['rebase_t'])
+    assert np.array_equal(np.asarray(p['v', 0].shapeas((4, 3))), g['shapeas'])
+    with pytest.raises(ValueError):
+        p.shapeas(())
+    c = m.process(c=(1., 2., 3.))
+    for q in (c.shapeas(p['v', 0])*p['v', 0], p['v', 0]*c.shapeas(p['v', 0])):
+        assert isinstance(q, m.process)
+        assert np.array_equal(np.asarray(q), g['const_times']) and np.array_equal(q.t, g['const_times_t'])
+    a, b = p.pcopy(), p.tcopy()
+    assert not np.shares_memory(a.t, p.t) and not np.shares_memory(a, p) and np.shares_memory(b, p)
+    assert np.shares_memory(p.xcopy().t, p.t)
+    for mode in ('mid', 'forward', 'backward'):
+        q = m.piecewise(g['t'], v=g['x'][..., 0], mode=mode)
+        assert np.array_equal(q(g['s']), g['piecewise_' + mode]), mode
+    with pytest.raises(ValueError):
+        m.piecewise(g['t'], v=g['x'][..., 0], mode='centre')
