@@ -77,6 +77,21 @@ class paths_generator:
     def exit(self, tt, xx):
         return tt, xx
 
+    # per-step hooks of the reference's Python loop (integration.py:392-474,
+    # 1154-1234): the kernel replaces them, so a user override cannot take effect
+    _stepping_hooks = ('begin', 'next', 'store', 'end', 'A', 'dZ', 'info_begin',
+                       'info_next', 'info_store', 'info_end')
+
+    def _check_no_python_stepping(self):
+        for name in self._stepping_hooks:
+            f = getattr(type(self), name, None)
+            if f is not None and not getattr(f, '__module__', '').startswith(__package__):
+                raise NotImplementedError(
+                    '{}.{} is a Python per-step hook: the integration runs as '
+                    'one CUDA kernel and cannot call it (no CPU stepping path). '
+                    "Available device schemes: method='euler' | 'milstein'"
+                    .format(type(self).__name__, name))
+
     def _device_run(self, tt, grid):
         raise NotImplementedError(
             '{} does not define a device integration: the CUDA path runs SDE '
@@ -123,6 +138,7 @@ class paths_generator:
         if self.getinfo:
             self.info.update(t0=tt[i0], tmin=tt[0], tmax=tt[-1],
                              computed_steps=0, stored_steps=0)
+        self._check_no_python_stepping()
         xx = self._device_run(tt, grid)
         return self.exit(tt_asis, xx)
 

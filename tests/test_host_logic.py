@@ -304,3 +304,30 @@ def test_kfunc_parameter_management():
     Q = P(paths=20, steps=7)
     assert (P.paths, Q.paths, Q.params['steps']) == (10, 20, 7)
     assert isinstance(Q, m.heston_process) and Q.params['rho'] == -.7
+
+
+def test_python_stepping_hooks_fail_loudly():
+    """A user-written ``next`` (the reference's plug point for Python
+    integration schemes, quickguide.rst:474-498) or per-step ``info_next``
+    cannot run inside the kernel: NotImplementedError before any device work,
+    never a silent Euler run."""
+    import sdepy_b200 as m
+
+    class my_integrator(m.integrator):
+        def next(self):
+            pass
+
+    class my_SDE(m.SDE):
+        def sde(self, t, x):
+            return {'dt': 0, 'dw': x}
+
+    class rk(my_SDE, my_integrator):
+        pass
+
+    class chatty(my_SDE, m.integrator):
+        def info_next(self):
+            pass
+
+    for cls, hook in ((rk, 'next'), (chatty, 'info_next')):
+        with pytest.raises(NotImplementedError, match=hook):
+            cls(paths=10, x0=1., steps=5)((0., 1.))
