@@ -59,6 +59,10 @@ ALGO_FP64_INSTR_PER_PATH_STEP = 100
 # no-store path of integrate_lean_kernel<HestonSDE<1,false>>, SASS count,
 # confirmed by ncu sm__inst_executed_pipe_fp64.sum / path-steps = 53.5
 N64_PER_PATH_STEP = 53
+# dram__bytes_read.sum + dram__bytes_write.sum of integrate_lean_kernel<Heston> from the
+# ncu --set full capture in profiles/r01_ncu_integrate_lean_heston.csv (1e7 paths x 252
+# steps per launch: 80 KB + 23 KB -- tables in, per-CTA partial sums out; nothing per path)
+NCU_DRAM_BYTES_PER_LAUNCH = 103156
 
 
 def parse():
@@ -311,7 +315,8 @@ def run_ours(a):
             'clocks': clocks,
             'roofline': {
                 'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf,
-                'unit': 'TFLOP/s', 'frac': achieved_tf/peak_tf, 'traffic': None,
+                'unit': 'TFLOP/s', 'frac': achieved_tf/peak_tf,
+                'traffic': NCU_DRAM_BYTES_PER_LAUNCH,
                 'executed': {'fp64_instr_per_path_step': N64_PER_PATH_STEP,
                              'achieved': executed_tf, 'frac': executed_tf/peak_tf},
                 'note': 'per GPU. achieved = ALGORITHMIC work (SURVEY 8d: %d FP64-pipe '
