@@ -13,8 +13,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(CSRC, 'libsdeb.so')
-SOURCES = ['sdeb.cu', 'sdeb_models_heston.cu', 'sdeb_models_linear.cu',
-           'sdeb_models_meanrev.cu']
+N_MODEL_UNITS = 11          # = SDEB_N_UNITS in sdeb_internal.h
+# (source, object stem, extra flags): sdeb_models.cu is compiled once per unit
+UNITS = [('sdeb.cu', 'sdeb', [])] + [
+    ('sdeb_models.cu', 'sdeb_models_%d' % k, ['-DSDEB_UNIT=%d' % k])
+    for k in range(N_MODEL_UNITS)]
+SOURCES = ['sdeb.cu', 'sdeb_models.cu']
 DEPS = SOURCES + ['sde_engine.cuh', 'sdeb_internal.h',
                   os.path.join('..', '..', 'include', 'sdeb.h')]
 NVCC_FLAGS = ['-Xcompiler', '-fPIC', '-O3', '-std=c++17',
@@ -42,19 +46,28 @@ def build(force=False, verbose=False):
     extra = os.environ.get('SDEB_NVCC_FLAGS', '').split()
     objdir = os.path.join(CSRC, 'build')
     os.makedirs(objdir, exist_ok=True)
-    procs = []
-    for src in SOURCES:     # one nvcc per translation unit, in parallel
-        obj = os.path.join(objdir, src.replace('.cu', '.o'))
-        cmd = [nvcc, '-c'] + NVCC_FLAGS + extra + (['-Xptxas=-v'] if verbose else []) + [
-            '-o', obj, os.path.join(CSRC, src)]
-        if verbose:
-            print(' '.join(cmd))
-        procs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE,
-                                                 stderr=subprocess.STDOUT, text=True)))
-    objs = []
-    for cmd, obj, proc in procs:
+    jobs = []
+    for src, stem, flags in UNITS:
+        obj = os.path.join(objdir, stem + '.o')
+        cmd = [nvcc, '-c'] + NVCC_FLAGS + extra + flags + (
+            ['-Xptxas=-v'] if verbose else []) + ['-o', obj, os.path.join(CSRC, src)]
+        jobs.append((cmd, obj))
+    # one nvcc per unit, as many at a time as there are cores
+    width = max(1, os.cpu_count() or 1)
+    objs, running = [], []
+    pending = list(jobs)
+    while pending or running:
+        while pending and len(running) < width:
+            cmd, obj = pending.pop(0)
+            if verbose:
+                print(' '.join(cmd))
+            running.append((cmd, obj, subprocess.Popen(
+                cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        cmd, obj, proc = running.pop(0)
         out, _ = proc.communicate()
         if proc.returncode != 0:
+            for _, _, other in running:
+                other.kill()
             raise RuntimeError('nvcc failed: %s\n%s' % (' '.join(cmd), out))
         if verbose:
             print(out)

@@ -71,8 +71,12 @@ static bool lookup_model(int64_t model, int64_t n, int64_t jit_handle, ModelInfo
         mi = it->second.mi;
         return true;
     }
-    return sdeb_lookup_heston(model, n, mi) || sdeb_lookup_linear(model, n, mi) ||
-           sdeb_lookup_meanrev(model, n, mi);
+    return sdeb_lookup_unit_0(model, n, mi) || sdeb_lookup_unit_1(model, n, mi) ||
+           sdeb_lookup_unit_2(model, n, mi) || sdeb_lookup_unit_3(model, n, mi) ||
+           sdeb_lookup_unit_4(model, n, mi) || sdeb_lookup_unit_5(model, n, mi) ||
+           sdeb_lookup_unit_6(model, n, mi) || sdeb_lookup_unit_7(model, n, mi) ||
+           sdeb_lookup_unit_8(model, n, mi) || sdeb_lookup_unit_9(model, n, mi) ||
+           sdeb_lookup_unit_10(model, n, mi);
 }
 
 // ---------------------------------------------------------------------------

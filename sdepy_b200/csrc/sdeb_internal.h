@@ -22,8 +22,10 @@ static ModelInfo info_of() {
     return mi;
 }
 
-// one registry function per translation unit (the kernels are instantiated
-// where they are registered, so the units compile in parallel)
-bool sdeb_lookup_linear(int64_t model, int64_t n, ModelInfo& mi);
-bool sdeb_lookup_meanrev(int64_t model, int64_t n, ModelInfo& mi);
-bool sdeb_lookup_heston(int64_t model, int64_t n, ModelInfo& mi);
+// one registry function per compiled unit of sdeb_models.cu (the kernels are
+// instantiated where they are registered, so the units compile in parallel)
+#define SDEB_N_UNITS 11
+#define SDEB_DECL_UNIT(k) bool sdeb_lookup_unit_##k(int64_t model, int64_t n, ModelInfo& mi);
+SDEB_DECL_UNIT(0) SDEB_DECL_UNIT(1) SDEB_DECL_UNIT(2) SDEB_DECL_UNIT(3) SDEB_DECL_UNIT(4)
+SDEB_DECL_UNIT(5) SDEB_DECL_UNIT(6) SDEB_DECL_UNIT(7) SDEB_DECL_UNIT(8) SDEB_DECL_UNIT(9)
+SDEB_DECL_UNIT(10)
