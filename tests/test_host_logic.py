@@ -331,3 +331,69 @@ def test_python_stepping_hooks_fail_loudly():
     for cls, hook in ((rk, 'next'), (chatty, 'info_next')):
         with pytest.raises(NotImplementedError, match=hook):
             cls(paths=10, x0=1., steps=5)((0., 1.))
+
+
+def test_sde_return_value_errors_follow_reference():
+    """Run-time error conventions of the reference (tests/test_integrator.py:
+    416-485): TypeError for a non-dict / non-tuple sde value, KeyError for an
+    unknown differential, ValueError for a wrong number of equations,
+    IndexError for a bad i0, ValueError for a bad timeline.  All raised while
+    the equation is traced, before any device work."""
+    import sdepy_b200 as m
+    t = np.linspace(0., 1., 5)
+
+    class f_process(m.SDE, m.integrator):
+        def sde(self, t, x):
+            return {'dt': 1, 'dw': 1}
+
+    f_process.sde = lambda self, t, x: x
+    with pytest.raises(TypeError):
+        f_process(x0=1, paths=11, steps=30)(t)
+    f_process.sde = lambda self, t, x: {'dt': 1, 'dzzz': 1}
+    with pytest.raises(KeyError):
+        f_process(x0=1, paths=11, steps=30)(t)
+
+    @m.integrate(q=2, sources=('dt', 'dw'))
+    def g_process(t, x, y):
+        return {'dt': 1, 'dw': 1}, {'dt': 1}
+    assert g_process.q == 2
+    g_process.sde = lambda self, t, x, y: {'dt': 1, 'dw': 1}
+    with pytest.raises(TypeError):
+        g_process(x0=(1,)*2, paths=11, steps=30)(t)
+    g_process.sde = lambda self, t, x, y: ({'dt': 1, 'dw': 1},)
+    with pytest.raises(ValueError):
+        g_process(x0=(1,)*2, paths=11, steps=30)(t)
+    g_process.sde = lambda self, t, x, y: ({'dt': 1}, {'dzzz': 1})
+    with pytest.raises(KeyError):
+        g_process(x0=(1,)*2, paths=11, steps=30)(t)
+
+    # declared q / sources: no test evaluation of the function
+    @m.integrate(q=0, sources={'dt', 'dw'})
+    def never_called(t, x):
+        raise ValueError
+
+    def bad_q():
+        @m.integrate(q=1)
+        def h(t, x=1., y=1.):
+            return {'dt': 1}, {'dw': 1}
+
+    def bad_sources():
+        @m.integrate(sources={'dw'})
+        def h(t, x=1., y=1.):
+            return {'dt': 1}, {'dw': 1}
+
+    def failing():
+        @m.integrate
+        def h(t, x):
+            raise ValueError
+
+    for err in (bad_q, bad_sources, failing):
+        with pytest.raises(TypeError):
+            err()
+
+    P = m.lognorm_process(paths=3, i0=7)
+    with pytest.raises(IndexError):
+        P(t)
+    for bad in (np.zeros((2, 2)), (0., 1., .5)):
+        with pytest.raises(ValueError):
+            m.lognorm_process(paths=3)(bad)
