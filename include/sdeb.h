@@ -266,6 +266,11 @@ int sdeb_fp64_peak(int64_t iters, double* dfma_per_second, void* stream);
  * integration.py:1843-1955): `model_source` defines `struct UserModel` with
  * the functor interface of sde_engine.cuh; the engine source is prepended by
  * the caller.  Returns a handle for sdeb_problem.jit_handle.
+ * Compilation is staged: this call builds the hot-configuration kernel and the
+ * model dimensions (-DSDEB_JIT_NO_GENERAL); sdeb_plan / sdeb_integrate compile
+ * the general kernel on first use, one sweep variant (noise mode x record
+ * residency) at a time (-DSDEB_JIT_NO_LEAN -DSDEB_SWEEPS=<bit>), and keep it
+ * with the handle.  A problem with n_paths == 0 only queries the dimensions.
  */
 int sdeb_jit_compile(const char* source, const char* model_type,
                      int64_t* handle, char* log, int64_t log_bytes);

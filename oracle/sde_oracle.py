@@ -259,7 +259,7 @@ def generic_replay(sde, params, x0, grid, where, dW, log=False,
     return np.exp(xx) if log else xx
 
 
-def system_replay(sde, q, params, x0s, grid, where, dW, addaxis):
+def system_replay(sde, q, params, x0s, grid, where, dW, addaxis, dN=None, dJ=None):
     """Replay driver for a user system ``sde(t, x1..xq, **params) -> (dict,)*q``
     (``SDEs``, integration.py:1584-1835).  The q equations are stacked along a
     new axis -2 (``addaxis``) or along the last axis of vshape, equation k
@@ -287,7 +287,14 @@ def system_replay(sde, q, params, x0s, grid, where, dW, addaxis):
         As = sde(s, *unpack(X), **_at(params, s))
         ids = sorted(set().union(*(a.keys() for a in As)))
         terms = [(pack(tuple(a.get(k, 0) for a in As)), k) for k in ids]
-        X = _euler_sum(X, terms, {'dt': ds, 'dw': dW[n]})
+        # the reference sums in the iteration order of a set of ids (1725-1729);
+        # sorted order is the convention of the kernel and of the fixtures
+        dz = {'dt': ds, 'dw': dW[n]}
+        if dN is not None:
+            dz['dn'] = dN[n]
+        if dJ is not None:
+            dz['dj'] = dJ[n]
+        X = _euler_sum(X, terms, dz)
         if n + 1 in out_of:
             rows.append(X.copy())
     return tuple(np.stack([unpack(r)[k] for r in rows]) for k in range(q))

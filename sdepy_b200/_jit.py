@@ -305,15 +305,24 @@ def _compile(source, name):
 
 
 # general entry + lean entry (Philox, one constant-bank record; own register budget)
+# The library compiles this source in stages (sdeb_jit_compile): first the
+# lean entry alone (-DSDEB_JIT_NO_GENERAL), then, on demand, a general entry
+# holding the single sweep variant a run needs (-DSDEB_JIT_NO_LEAN
+# -DSDEB_SWEEPS=<bit>): a general kernel with all six variants costs ~6x the
+# NVRTC time of one.
 JIT_ENTRIES = [
-    'extern "C" __global__ void __launch_bounds__(SDEB_THREADS, 1)',
+    '#ifndef SDEB_JIT_NO_GENERAL',
+    'extern "C" __global__ void __launch_bounds__(SDEB_THREADS, SDEB_MIN_BLOCKS)',
     'sdeb_jit_entry(const sdeb::KArgs a) { sdeb::integrate_body<sdeb::UserModel, false>(a); }',
+    '#endif',
+    '#ifndef SDEB_JIT_NO_LEAN',
     'extern "C" __global__ void __launch_bounds__(SDEB_THREADS, 1)',
     'sdeb_jit_entry_lean(const sdeb::KArgs a) {',
     '    if (sdeb::UserModel::NPC + (sdeb::UserModel::NDW > 1 ? sdeb::UserModel::NDW *',
     '        (sdeb::UserModel::NDW + 1) / 2 : 0) <= sdeb::MAX_CBANK_PARAMS)',
     '        sdeb::integrate_body<sdeb::UserModel, true>(a);',
     '}',
+    '#endif',
     '']
 
 PRESET_FUNCTORS = {
@@ -359,10 +368,6 @@ class _traced:
     @property
     def _nvars(self):
         return self.q if self._system else 1
-
-    @property
-    def _rec_comps(self):
-        return 1 if self._system else self._lanes()[1]
 
     def _param_target(self):
         return self.vshape if self._system else self.wshape
@@ -418,7 +423,7 @@ class _traced:
         mil = self._milstein_nodes(tr, roots) if milstein else [None]*len(roots)
         sig = self._traced_signature(tr, roots, mil)
         nleaf = len(tr.leaves)
-        src = (self._codegen_system if self._system else self._codegen_single)(tr, roots, mil)
+        src = self._codegen(tr, roots, mil)
         handle = _compile(engine_source() + PRELUDE + src, type(self).__name__)
         self._jit = dict(handle=handle, sig=sig, nleaf=nleaf, milstein=milstein,
                          source=src)
@@ -460,96 +465,100 @@ class _traced:
         corr_t = not replay and isinstance(dw, wiener_source) and callable(dw.corr)
         jumps_t = spec.jumps and not replay and self._jumps_time_dependent()
         n = seg.n_steps if (tdep or corr_t or jumps_t) and seg.n_steps else 1
-        ncomp = self._rec_comps
+        nw = spec.nw
+        elems = nw//self._nvars          # elements of the last axis owned by a lane
         blocks = []
         for i in range(n):
             s = seg.s[i] if seg.n_steps else 0.
             ds = seg.ds[i] if seg.n_steps else 0.
             leaves = vals[0] if (i == 0 or not tdep) else self._leaf_values(float(s))
+            # record = [elements x leaves] then, with jumps, [components x 6]
             cols = [lane_values(v, lanes, 'SDE parameter', paths=self.paths) for v in leaves]
-            if spec.jumps:
-                zero = np.zeros(spec.groups*ncomp)
-                if replay:
-                    cols += [zero]*6
-                else:
-                    mid = s + ds/2
-                    if 'dn' in self.sources:     # plain Poisson: unit jump sizes
-                        lam_src = dj
-                        kind, a, b, pa = _lib.LAW_UNIFORM, 1., 1., 0.
-                    else:
-                        lam_src = dj.dn
-                        kind, a, b, pa = dj.y.at(mid)
-                    lam = lane_values(lam_src.lam_at(mid), lanes, 'lam', paths=self.paths)
-                    cols += [lam, zero, zero + kind] + [
-                        lane_values(z, lanes, 'jump law parameter', paths=self.paths)
-                        for z in (a, b, pa)]
-            block = (stack_lane_columns(cols, spec.groups, ncomp) if cols
+            block = (stack_lane_columns(cols, spec.groups, elems) if cols
                      else np.zeros((spec.groups, 0)))
+            if spec.jumps:
+                block = _join_blocks(block, self._jump_block(spec, dj, s, ds, replay))
             L = None
             if spec.nchol and not replay and isinstance(dw, wiener_source):
                 L = dw.chol_at(s + ds/2)
             blocks.append((block, _engine.chol_entries(L, spec.ndw)))
         return _engine.assemble_records(blocks, spec)
 
+    def _jump_block(self, spec, dj, s, ds, replay):
+        """[groups, 6*nw (, paths)]: per working component lam, (reserved), law,
+        a, b, pa -- intensity and law sampled at the step midpoint
+        (infrastructure.py:1630, 2031)."""
+        nw = spec.nw
+        if replay:
+            return np.zeros((spec.groups, 6*nw))
+        mid = s + ds/2
+        if 'dn' in self.sources:         # plain Poisson: unit jump sizes
+            lam_src = dj
+            kind, a, b, pa = _lib.LAW_UNIFORM, 1., 1., 0.
+        else:
+            lam_src = dj.dn
+            kind, a, b, pa = dj.y.at(mid)
+        cols = []
+        for z in (lam_src.lam_at(mid), 0., float(kind), a, b, pa):
+            z = np.asarray(z, dtype=float)
+            if z.ndim == len(self.wshape) + 1 and z.shape[-1] == self.paths:
+                full = np.broadcast_to(z, self.wshape + (self.paths,))
+            else:
+                if z.ndim == len(self.wshape) + 1 and z.shape[-1] == 1:
+                    z = z[..., 0]
+                full = np.broadcast_to(z, self.wshape)[..., np.newaxis]
+            cols.append(self._to_lanes(full).reshape((spec.groups, nw, -1)))
+        width = max(c.shape[-1] for c in cols)
+        cols = [np.broadcast_to(c, (spec.groups, nw, width)) for c in cols]
+        block = np.stack(cols, axis=2).reshape((spec.groups, 6*nw, width))
+        return block[..., 0] if width == 1 else block
+
     # ---- code generation ----------------------------------------------------
-    def _codegen_single(self, tr, roots, mil):
-        lead, m = self._lanes()
-        ids = [k for k, _ in roots[0]]
-        unknown = set(ids) - {'dt', 'dw', 'dj', 'dn'}
+    def _codegen(self, tr, roots, mil):
+        """UserModel functor.  A lane owns ``elems`` elements of the last axis,
+        each with ``q`` variables (q = 1 for a single equation; elems = 1
+        unless the Wiener components are coupled by a correlation matrix);
+        variable k of element h is working component k*elems + h -- the
+        reference's own stacking (integration.py:1735-1757)."""
+        lead, nw = self._lanes()
+        q = self._nvars
+        elems = nw//q
+        ids = set(k for r in roots for k, _ in r)
+        unknown = ids - {'dt', 'dw', 'dj', 'dn'}
         if unknown:
             raise NotImplementedError('differentials {} have no device '
                                       'implementation'.format(unknown))
         jumps = self._jump_source() is not None
         nleaf = len(tr.leaves)
-        per = nleaf + (6 if jumps else 0)
-        em = emitter(lambda k: 'p[%d*c + %d]' % (per, k), lambda i: 'x[c]')
-        terms = []
-        for k, nd in roots[0]:
-            dz = {'dt': 'ds', 'dw': 'dw[c]', 'dj': 'dj[c]', 'dn': 'dj[c]'}[k]
-            terms.append('xmul(%s, %s)' % (em.ref(nd), dz))
-        inc = terms[0]
-        for tm in terms[1:]:
-            inc = 'xadd(%s, %s)' % (inc, tm)
-        body = list(em.lines)
-        em.lines = []
-        body.append('double xn = xadd(x[c], %s);' % inc)
-        if mil[0] is not None:
-            body += _flush(em, mil[0])
-            body.append('xn = xadd(xn, xmul(%s, xsub(xmul(dw[c], dw[c]), ds)));'
-                        % em.ref(mil[0]))
-        body.append('x[c] = xn;')
-        return _model_source(m, m, per*m, jumps, per, nleaf, body, self.log, loop=True)
 
-    def _codegen_system(self, tr, roots, mil):
-        q = self.q
-        if 'dj' in self.sources or 'dn' in self.sources:
-            raise NotImplementedError('jumps in traced systems of SDEs')
-        nleaf = len(tr.leaves)
-        em = emitter(lambda k: 'p[%d]' % k, lambda i: 'x[%d]' % i)
-        news = []
-        for i, r in enumerate(roots):
+        def comp(k):
+            return '%d*E + h' % k if elems > 1 else '%d' % k
+        em = emitter(lambda j: 'p[%d*h + %d]' % (nleaf, j),
+                     lambda k: 'x[%s]' % comp(k))
+        incs = []
+        for k, r in enumerate(roots):
             terms = []
-            for k, nd in r:
-                if k not in ('dt', 'dw'):
-                    raise NotImplementedError('differential ' + k)
-                dz = 'ds' if k == 'dt' else 'dw[%d]' % i
+            for ident, nd in r:
+                dz = {'dt': 'ds', 'dw': 'dw[%s]' % comp(k), 'dj': 'dj[%s]' % comp(k),
+                      'dn': 'dj[%s]' % comp(k)}[ident]
                 terms.append('xmul(%s, %s)' % (em.ref(nd), dz))
             inc = terms[0] if terms else '0.0'
             for tm in terms[1:]:
                 inc = 'xadd(%s, %s)' % (inc, tm)
-            news.append((i, inc))
+            incs.append(inc)
         body = list(em.lines)
         em.lines = []
-        for i, inc in news:
-            body.append('double xn%d = xadd(x[%d], %s);' % (i, i, inc))
-        for i in range(q):
-            if mil[i] is not None:
-                body += _flush(em, mil[i])
-                body.append('xn%d = xadd(xn%d, xmul(%s, xsub(xmul(dw[%d], dw[%d]), ds)));'
-                            % (i, i, em.ref(mil[i]), i, i))
-        for i in range(q):
-            body.append('x[%d] = xn%d;' % (i, i))
-        return _model_source(q, q, nleaf, False, 0, 0, body, self.log, loop=False)
+        for k, inc in enumerate(incs):
+            body.append('double xn%d = xadd(x[%s], %s);' % (k, comp(k), inc))
+        for k in range(q):
+            if mil[k] is not None:
+                body += _flush(em, mil[k])
+                body.append('xn{0} = xadd(xn{0}, xmul({1}, xsub(xmul(dw[{2}], dw[{2}]), ds)));'
+                            .format(k, em.ref(mil[k]), comp(k)))
+        for k in range(q):
+            body.append('x[%s] = xn%d;' % (comp(k), k))
+        npc = elems*nleaf + (6*nw if jumps else 0)
+        return _model_source(nw, nw, npc, jumps, 6, elems*nleaf, body, self.log, elems)
 
 
 def _flush(em, nd):
@@ -561,20 +570,27 @@ def _flush(em, nd):
     return new
 
 
-def _model_source(nw, ndw, npc, jumps, jp_stride, jp_off, body, log, loop):
+def _join_blocks(a, b):
+    """Concatenate two record blocks [groups, n (, paths)] along axis 1."""
+    if a.ndim != b.ndim:
+        paths = (a if a.ndim == 3 else b).shape[-1]
+        a, b = (np.broadcast_to(z[..., np.newaxis], z.shape + (paths,)) if z.ndim == 2 else z
+                for z in (a, b))
+    return np.concatenate((a, b), axis=1)
+
+
+def _model_source(nw, ndw, npc, jumps, jp_stride, jp_off, body, log, elems):
     lines = ['namespace sdeb {', 'struct UserModel {',
              '    enum { NW = %d, NDW = %d, NX = %d, NPC = %d, NCNT = %d, JUMPS = %d,'
              % (nw, ndw, nw, npc, nw if jumps else 0, int(jumps)),
              '           JP_STRIDE = %d, JP_OFF = %d };' % (jp_stride, jp_off),
              '    static __device__ __forceinline__ void step(double (&x)[NW], const double* p,',
              '            double ds, const double* dw, const double* dj, int (&cnt)[NCNT + 1]) {']
-    if loop:
-        lines.append('#pragma unroll')
-        lines.append('        for (int c = 0; c < NW; ++c) {')
-        lines += ['            ' + b for b in body]
-        lines.append('        }')
-    else:
-        lines += ['        ' + b for b in body]
+    lines.append('        enum { E = %d };' % elems)
+    lines.append('#pragma unroll')
+    lines.append('        for (int h = 0; h < E; ++h) {')
+    lines += ['            ' + b for b in body]
+    lines.append('        }')
     lines += ['    }',
               '    static __device__ __forceinline__ void emit(const double (&x)[NW], double (&v)[NX]) {',
               '#pragma unroll',

@@ -55,8 +55,12 @@ extern "C" int sdeb_device_info(int64_t* sm_count, int64_t* cc_major, int64_t* c
 // model registry: pre-instantiated presets live in sdeb_models_*.cu
 // ---------------------------------------------------------------------------
 struct JitModule {
-    cudaLibrary_t lib;
-    cudaKernel_t kernel, kernel_lean;
+    std::string source, name;
+    cudaLibrary_t lib;                 // stage 0: lean entry + dims
+    cudaKernel_t kernel_lean;
+    cudaLibrary_t glib[6];             // general entry, one library per sweep variant
+    cudaKernel_t gkernel[6];
+    bool ghave[6];
     ModelInfo mi;
 };
 static std::mutex g_jit_mutex;
@@ -105,6 +109,13 @@ static bool use_lean(const sdeb_problem* p, const ModelInfo& mi) {
            !p->anti_dw_half && !p->anti_dj_half && !p->params_per_path;
 }
 
+// index of the sweep variant integrate_body takes for this problem (SDEB_SWEEPS bit)
+static int sweep_variant(const sdeb_problem* p) {
+    int noise = p->noise == SDEB_NOISE_REPLAY ? 1 : (p->dW_dump ? 2 : 0);
+    return 2 * noise + (p->n_psteps > 1 ? 1 : 0);
+}
+static int jit_general_kernel(int64_t handle, int variant, const void** fn);
+
 static int plan_impl(const sdeb_problem* p, sdeb_plan_t* plan, ModelInfo& mi, bool need_device) {
     if (!p || !plan) return fail(SDEB_EINVAL, "null problem/plan");
     if (p->abi_version != SDEB_ABI_VERSION)
@@ -133,9 +144,15 @@ static int plan_impl(const sdeb_problem* p, sdeb_plan_t* plan, ModelInfo& mi, bo
     int64_t tiles = ((p->n_paths + kThreads - 1) / kThreads) * p->n_groups;
     int sm = 148, occ = 2;
     int dev = 0;
-    const void* fn = use_lean(p, mi) ? mi.fn_lean : mi.fn;
     cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) {
+    if (e == cudaSuccess && p->model == SDEB_MODEL_JIT && !use_lean(p, mi) && p->n_paths > 0) {
+        // NVRTC models: compile the general kernel of this run's sweep variant
+        // (a problem without paths is a query for the model's dimensions)
+        int rcj = jit_general_kernel(p->jit_handle, sweep_variant(p), &mi.fn);
+        if (rcj) return rcj;
+    }
+    const void* fn = use_lean(p, mi) ? mi.fn_lean : mi.fn;
+    if (e == cudaSuccess && fn) {
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
         if (plan->smem_bytes > 32 * 1024)   // + ~10 KB of static shared memory
             cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -144,7 +161,7 @@ static int plan_impl(const sdeb_problem* p, sdeb_plan_t* plan, ModelInfo& mi, bo
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, kThreads,
                                                           (size_t)plan->smem_bytes) == cudaSuccess && o > 0)
             occ = o;
-    } else {
+    } else if (e != cudaSuccess) {
         cudaGetLastError();
         if (need_device) return fail(SDEB_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(e));
     }
@@ -1014,29 +1031,22 @@ static int load_nvrtc() {
     return SDEB_OK;
 }
 
-// `source` = engine header + model definition + an
-//   extern "C" __global__ void sdeb_jit_entry(const sdeb::KArgs a)
-// wrapper plus  extern "C" __constant__ int sdeb_jit_dims[6] = {NW,NDW,NX,NPC,NCNT,JUMPS};
-// (the Python side generates all of it, sdepy_b200/_jit.py); `model_type` is only
-// used as the NVRTC program name.
-extern "C" int sdeb_jit_compile(const char* source, const char* model_type, int64_t* handle,
-                                char* log, int64_t log_bytes) {
-    if (!source || !handle) return fail(SDEB_EINVAL, "sdeb_jit_compile: null argument");
-    if (log && log_bytes > 0) log[0] = 0;
+static int nvrtc_cubin(const std::string& source, const std::string& name,
+                       const std::vector<std::string>& defines, std::vector<char>& cubin,
+                       std::string& plog) {
     int rc = load_nvrtc();
     if (rc) return rc;
     nvrtcProgram_t prog;
-    nvrtcResult_t r = g_nvrtc.CreateProgram(&prog, source, model_type ? model_type : "sdeb_jit.cu",
-                                            0, NULL, NULL);
+    nvrtcResult_t r = g_nvrtc.CreateProgram(&prog, source.c_str(), name.c_str(), 0, NULL, NULL);
     if (r) return fail(SDEB_EJIT, std::string("nvrtcCreateProgram: ") + g_nvrtc.GetErrorString(r));
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17",
-                          "-default-device"};
-    r = g_nvrtc.CompileProgram(prog, 4, opts);
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17",
+                                     "-default-device"};
+    for (const std::string& d : defines) opts.push_back(d.c_str());
+    r = g_nvrtc.CompileProgram(prog, (int)opts.size(), opts.data());
     size_t lsz = 0;
     g_nvrtc.GetProgramLogSize(prog, &lsz);
-    std::string plog(lsz, 0);
+    plog.assign(lsz, 0);
     if (lsz > 1) g_nvrtc.GetProgramLog(prog, &plog[0]);
-    if (log && log_bytes > 0) { strncpy(log, plog.c_str(), (size_t)log_bytes - 1); log[log_bytes - 1] = 0; }
     if (r) {
         g_nvrtc.DestroyProgram(&prog);
         return fail(SDEB_EJIT, std::string("nvrtcCompileProgram: ") + g_nvrtc.GetErrorString(r) +
@@ -1044,20 +1054,41 @@ extern "C" int sdeb_jit_compile(const char* source, const char* model_type, int6
     }
     size_t csz = 0;
     g_nvrtc.GetCUBINSize(prog, &csz);
-    std::vector<char> cubin(csz);
+    cubin.resize(csz);
     g_nvrtc.GetCUBIN(prog, cubin.data());
     g_nvrtc.DestroyProgram(&prog);
+    return SDEB_OK;
+}
 
+// `source` = engine header + model definition + the entry wrappers
+//   extern "C" __global__ void sdeb_jit_entry(const sdeb::KArgs a)       (#ifndef SDEB_JIT_NO_GENERAL)
+//   extern "C" __global__ void sdeb_jit_entry_lean(const sdeb::KArgs a)  (#ifndef SDEB_JIT_NO_LEAN)
+// plus  extern "C" __constant__ int sdeb_jit_dims[6] = {NW,NDW,NX,NPC,NCNT,JUMPS};
+// (the Python side generates all of it, sdepy_b200/_jit.py); `model_type` is only
+// used as the NVRTC program name.  Compiled here: the lean entry and the
+// dimensions.  The general entry is compiled by the first sdeb_integrate that
+// needs it, one sweep variant (noise mode x record residency) at a time.
+extern "C" int sdeb_jit_compile(const char* source, const char* model_type, int64_t* handle,
+                                char* log, int64_t log_bytes) {
+    if (!source || !handle) return fail(SDEB_EINVAL, "sdeb_jit_compile: null argument");
+    if (log && log_bytes > 0) log[0] = 0;
     JitModule jm;
+    jm.source = source;
+    jm.name = model_type ? model_type : "sdeb_jit.cu";
+    for (int k = 0; k < 6; ++k) jm.ghave[k] = false;
+    std::vector<char> cubin;
+    std::string plog;
+    int rc = nvrtc_cubin(jm.source, jm.name, {"-DSDEB_JIT_NO_GENERAL"}, cubin, plog);
+    if (log && log_bytes > 0) { strncpy(log, plog.c_str(), (size_t)log_bytes - 1); log[log_bytes - 1] = 0; }
+    if (rc) return rc;
     CUDA_TRY(cudaLibraryLoadData(&jm.lib, cubin.data(), NULL, NULL, 0, NULL, NULL, 0));
-    CUDA_TRY(cudaLibraryGetKernel(&jm.kernel, jm.lib, "sdeb_jit_entry"));
     void* dptr = NULL;
     size_t dbytes = 0;
     CUDA_TRY(cudaLibraryGetGlobal(&dptr, &dbytes, jm.lib, "sdeb_jit_dims"));
     int dims[6];
     if (dbytes < sizeof dims) return fail(SDEB_EJIT, "sdeb_jit_dims has the wrong size");
     CUDA_TRY(cudaMemcpy(dims, dptr, sizeof dims, cudaMemcpyDeviceToHost));
-    jm.mi.fn = (const void*)jm.kernel;
+    jm.mi.fn = NULL;
     jm.mi.fn_lean = NULL;
     if (cudaLibraryGetKernel(&jm.kernel_lean, jm.lib, "sdeb_jit_entry_lean") == cudaSuccess &&
         dims[3] + (dims[1] > 1 ? dims[1] * (dims[1] + 1) / 2 : 0) <= MAX_CBANK_PARAMS)
@@ -1072,11 +1103,34 @@ extern "C" int sdeb_jit_compile(const char* source, const char* model_type, int6
     return SDEB_OK;
 }
 
+static int jit_general_kernel(int64_t handle, int variant, const void** fn) {
+    std::lock_guard<std::mutex> lock(g_jit_mutex);
+    auto it = g_jit.find(handle);
+    if (it == g_jit.end()) return fail(SDEB_EINVAL, "unknown JIT handle");
+    JitModule& jm = it->second;
+    if (variant < 0 || variant >= 6) return fail(SDEB_EINVAL, "bad sweep variant");
+    if (!jm.ghave[variant]) {
+        char def[64];
+        snprintf(def, sizeof def, "-DSDEB_SWEEPS=%d", 1 << variant);
+        std::vector<char> cubin;
+        std::string plog;
+        int rc = nvrtc_cubin(jm.source, jm.name, {"-DSDEB_JIT_NO_LEAN", def}, cubin, plog);
+        if (rc) return rc;
+        CUDA_TRY(cudaLibraryLoadData(&jm.glib[variant], cubin.data(), NULL, NULL, 0, NULL, NULL, 0));
+        CUDA_TRY(cudaLibraryGetKernel(&jm.gkernel[variant], jm.glib[variant], "sdeb_jit_entry"));
+        jm.ghave[variant] = true;
+    }
+    *fn = (const void*)jm.gkernel[variant];
+    return SDEB_OK;
+}
+
 extern "C" int sdeb_jit_release(int64_t handle) {
     std::lock_guard<std::mutex> lock(g_jit_mutex);
     auto it = g_jit.find(handle);
     if (it == g_jit.end()) return fail(SDEB_EINVAL, "sdeb_jit_release: unknown handle");
     cudaLibraryUnload(it->second.lib);
+    for (int k = 0; k < 6; ++k)
+        if (it->second.ghave[k]) cudaLibraryUnload(it->second.glib[k]);
     g_jit.erase(it);
     return SDEB_OK;
 }

@@ -785,23 +785,27 @@ class SDEs(SDE):
     def result(self, tt, XX):
         return tuple(_wrap(tt, xx) for xx in self.unpack(XX))
 
+    def _stacked_coupled(self):
+        """addaxis=False with a correlated Wiener source: the correlation
+        matrix couples the whole stacked axis (q*d components)."""
+        dw = self.sources.get('dw')
+        return (not self.addaxis and isinstance(dw, wiener_source)
+                and dw.corr is not None)
+
     def _lanes(self):
         """Traced systems: one lane owns the q variables of an element of
         vshape.  With addaxis=True they are adjacent in the working array;
         with addaxis=False variable k of element h sits at k*d + h along the
         last axis (reference 1735-1757) and ``_to_lanes`` / ``_from_lanes``
-        transpose between the two layouts on the way in and out."""
-        if not self.addaxis:
-            dw = self.sources.get('dw')
-            if isinstance(dw, wiener_source) and dw.corr is not None:
-                raise NotImplementedError(
-                    'a Wiener source correlated across the stacked axis of a '
-                    'traced system needs addaxis=True (one correlation matrix '
-                    'per element of vshape)')
+        transpose between the two layouts on the way in and out -- unless
+        the Wiener source is correlated along that axis: then one lane owns
+        all its q*d components, in the reference's own order."""
+        if self._stacked_coupled():
+            return self.vshape[:-1], self.wshape[-1]
         return self.vshape, self.q
 
     def _to_lanes(self, a, pre=0):
-        if self.addaxis:
+        if self.addaxis or self._stacked_coupled():
             return a
         v, q = self.vshape, self.q
         a = a.reshape(a.shape[:pre] + v[:-1] + (q, v[-1]) + a.shape[pre + len(v):])
@@ -809,7 +813,7 @@ class SDEs(SDE):
         return a.swapaxes(ax, ax + 1)
 
     def _from_lanes(self, a, tail):
-        if self.addaxis:
+        if self.addaxis or self._stacked_coupled():
             return super()._from_lanes(a, tail)
         v, q = self.vshape, self.q
         a = a.reshape(a.shape[:1] + v + (q,) + tail)

@@ -29,6 +29,15 @@ def user_system(t, x, y, mu=0., sigma=1., xi=1.):
     return ({'dt': mu*x, 'dw': y*x}, {'dt': sigma*(1. - y), 'dw': xi*y})
 
 
+def jump_system(t, x=0, y=0, k=1):
+    """Same equations as tests/golden/make_golden.py:jump_system."""
+    return ({'dt': x, 'dn': k, 'dw': y}, {'dt': 1, 'dn': k*y, 'dw': x - y})
+
+
+def k_of_t(t):
+    return .5 + .1*t
+
+
 HW = dict(factors=3, x0=((.01,), (0.,), (0.,)), theta=hw_theta,
           k=((.1,), (.5,), (1.,)), sigma=((.01,), (.008,), (.005,)),
           corr=hw_corr)

@@ -311,6 +311,39 @@ def time_axis_case():
     save('stats_time_axis', **out)
 
 
+def jump_system(t, x=0, y=0, k=1):
+    """2 equations with Poisson jumps and Wiener increments
+    (reference tests/test_integrator.py:312-327)."""
+    return ({'dt': x, 'dn': k, 'dw': y}, {'dt': 1, 'dn': k*y, 'dw': x - y})
+
+
+def k_of_t(t):
+    return .5 + .1*t
+
+
+def jump_system_case():
+    """User system with 'dt', 'dn' and 'dw' terms, time-dependent parameter,
+    intensity and correlation.  The reference sums the three terms in the
+    iteration order of a SET of ids (integration.py:1725-1729), i.e. in an
+    order that depends on the interpreter's string-hash seed; the kernel sums
+    in sorted-id order, so this fixture must be generated under a hash seed
+    where the two coincide (the script checks and says so)."""
+    cls = sdepy.integrate(q=2, sources={'dt', 'dn', 'dw'})(jump_system)
+    kw = dict(paths=41, steps=30, x0=(1., .5), k=k_of_t)
+    src = dict(lam=lambda t: 3. + t, rho=lambda t: -.5 + .1*t)
+    probe = cls(rng=np.random.default_rng(8), **kw, **src)
+    order = list(probe.A(0., np.ones((2, 41))).keys())
+    if order != sorted(order):
+        raise SystemExit('set order %s != sorted order: rerun with another '
+                         'PYTHONHASHSEED' % order)
+    rec_w, rec_n = recorder(probe.sources['dw']), recorder(probe.sources['dn'])
+    P = cls(dw=rec_w, dn=rec_n, **kw)
+    tt = np.linspace(0., 1., 7)
+    x, y = P(tt)
+    save('replay_system_jumps', tt=tt, grid=grid_of(P, tt), dW=np.stack(rec_w.dz),
+         dN=np.stack(rec_n.dz), out0=np.asarray(x), out1=np.asarray(y))
+
+
 CONTAINER_KEYS = {
     't_int': ('t', 2), 't_last': ('t', -1), 't_slice': ('t', slice(1, 4)),
     'p_int': ('p', 3), 'p_slice': ('p', slice(0, 5, 2)), 'p_list': ('p', [1, 3]),
@@ -346,6 +379,8 @@ def process_container_case():
 if __name__ == '__main__':
     if sys.argv[1:] == ['container']:
         process_container_case()
+    elif sys.argv[1:] == ['jumpsystem']:
+        jump_system_case()
     elif sys.argv[1:] == ['systems']:
         user_system_cases()
     elif sys.argv[1:] == ['timeaxis']:
@@ -355,3 +390,4 @@ if __name__ == '__main__':
         user_system_cases()
         time_axis_case()
         process_container_case()
+        jump_system_case()

@@ -233,3 +233,114 @@ def test_traced_sde_with_plain_poisson_differential():
     y = np.asarray(counter(paths=300, steps=51, x0=0., c=2.,
                            dn=m.replay_source(dn))((0., 1.)))[-1]
     assert np.array_equal(y, 2.*dn.sum(axis=0))
+
+
+def test_user_system_with_jumps_replay_bit_exact():
+    """Traced 2-equation system with Poisson ('dn') and Wiener terms and a
+    time-dependent coefficient: the reference's own output from its recorded
+    increments, bit for bit (golden fixture replay_system_jumps)."""
+    from tests.cases import jump_system, k_of_t
+    m = sd()
+    g = golden('replay_system_jumps')
+    cls = m.integrate(q=2, sources={'dt', 'dn', 'dw'})(jump_system)
+    P = cls(paths=g['dW'].shape[-1], steps=30, x0=(1., .5), k=k_of_t,
+            dw=m.replay_source(g['dW']), dn=m.replay_source(g['dN'].astype(float)))
+    x, y = P(g['tt'])
+    assert np.array_equal(np.asarray(x), g['out0'])
+    assert np.array_equal(np.asarray(y), g['out1'])
+
+
+def test_reference_test_SDE_cases():
+    """The calls of the reference's tests/test_integrator.py::test_SDE
+    (:185-404) with its shape assertions, plus moments where they are known:
+    systems with time-dependent rho / corr over a stacked axis, Poisson and
+    compound Poisson terms, four equations without 'dt', a shared
+    true_wiener_source, partially omitted terms."""
+    m = sd()
+    t = np.linspace(0., 1., 7)
+
+    def f(t, x=0, y=0, z=0, sigma=1., a=2.):
+        return ({'dt': a*x, 'dw': sigma*y}, {'dt': -y, 'dw': sigma}, {'dt': z, 'dw': 0.1*x})
+    args = dict(x0=(1, 2, 3), sigma=((.1,), (.2,)), a=lambda t: ((1 + t,), (2*t,)),
+                vshape=2, paths=11, steps=30)
+    for kw in (dict(rho=lambda t: (.01*t, .2, .3)),
+               dict(corr=lambda t: ((1, .01*t, .2, .3, .4, .5), (.01*t, 1, -.1, -.2, -.3, -.4),
+                                    (.2, -.1, 1, 0, .1, 0), (.3, -.2, 0, 1, .1, .2),
+                                    (.4, -.3, .1, .1, 1, 0), (.5, -.4, 0, .2, 0, 1)))):
+        for u in m.integrate(f)(**args, **kw)(t):
+            assert u.shape == (7, 2, 11) and np.isfinite(u).all()
+
+    # Poisson jumps, alone and with Wiener increments
+    def f(t, x=0, y=0, k=1):
+        return ({'dt': x, 'dn': k}, {'dt': 1, 'dn': k*y})
+    for u in m.integrate(f)(x0=(0., 0.), k=lambda t: .01*t, lam=lambda t: .2*t)(t):
+        assert u.shape == (7, 1)
+
+    @m.integrate(q=2, sources={'dt', 'dn'})
+    def f_process(t, x, y, k):
+        return f(t, x, y, k)
+    for u in f_process(x0=(0., 0.), k=lambda t: .01*t, lam=lambda t: .2*t, steps=30)(t):
+        assert u.shape == (7, 1)
+    # E[x(1)] of dx = x dt + k dn, x0 = 0, constant k and lam: k lam (e - 1)
+    x, y = f_process(x0=(0., 0.), k=.5, lam=3., steps=200, paths=200000, seed=5)(t)
+    want = .5*3.*(np.e - 1)
+    assert abs(x[-1].mean()/want - 1) < .02
+
+    def f(t, x=0, y=0, k=1):
+        return ({'dt': x, 'dn': k, 'dw': y}, {'dt': 1, 'dn': k*y, 'dw': x - y})
+    for u in m.integrate(f)(x0=(0., 0.), k=lambda t: .01*t, lam=lambda t: .2*t, rho=-.5)(t):
+        assert u.shape == (7, 1)
+
+    @m.integrate(q=2, sources={'dt', 'dn', 'dw'})
+    def f_process(t, x, y, k):
+        return f(t, x, y, k)
+    for u in f_process(x0=(0., 0.), k=lambda t: .01*t, lam=lambda t: .2*t,
+                       rho=lambda t: -.01*t, steps=30)(t):
+        assert u.shape == (7, 1)
+
+    # compound Poisson jumps with every jump law
+    def f(t, x=0, y=0, k=1):
+        return ({'dt': x, 'dj': k}, {'dt': 1, 'dj': k*y})
+    for u in m.integrate(f)(x0=(0., 0.), k=lambda t: .01*t, lam=lambda t: .2*t,
+                            y=m.uniform_rv(a=-1, b=lambda t: t))(t):
+        assert u.shape == (7, 1)
+
+    @m.integrate(q=2, sources={'dt', 'dj'})
+    def f_process(t, x, y, k):
+        return f(t, x, y, k)
+    for u in f_process(x0=(0., 0.), k=lambda t: .01*t, lam=lambda t: .2*t,
+                       y=m.exp_rv(a=-1), steps=30)(t):
+        assert u.shape == (7, 1)
+
+    def f(t, x=0, y=0, k=1):
+        return ({'dt': x, 'dj': k, 'dw': y}, {'dt': 1, 'dj': k*y, 'dw': x - y})
+    for u in m.integrate(f)(x0=(0., 0.), k=lambda t: .01*t, lam=lambda t: .2*t, rho=-.5,
+                            y=m.norm_rv(a=1, b=lambda t: 2 + t))(t):
+        assert u.shape == (7, 1)
+
+    @m.integrate(q=2, sources={'dt', 'dj', 'dw'})
+    def f_process(t, x, y, k):
+        return f(t, x, y, k)
+    for u in f_process(x0=(0., 0.), k=lambda t: .01*t, lam=lambda t: .2*t,
+                       rho=lambda t: -.01*t, y=m.double_exp_rv(a=1, b=2, pa=.1), steps=30)(t):
+        assert u.shape == (7, 1)
+
+    # four equations with no 'dt' term, correlated; then a shared true_wiener_source
+    def f(t, x=0, y=0, z=0, w=0):
+        return ({'dw': x}, {'dw': y}, {'dw': z}, {'dw': w})
+    rm4 = np.random.default_rng(1).random((4, 4))
+    corr4 = np.eye(4) + 0.1*(rm4 + rm4.T)
+    for u in m.integrate(f)(x0=(1,)*4, corr=corr4, paths=11, steps=30)(t):
+        assert u.shape == (7, 11)
+    tw = m.true_wiener_source(vshape=4, paths=11, corr=corr4)
+    xs1 = m.integrate(f)(x0=(1.,)*4, dw=tw, paths=11, steps=30)(t)
+    xs2 = m.integrate(f)(x0=(1.,)*4, dw=tw, paths=11, steps=30)(t)
+    for u, v in zip(xs1, xs2):
+        assert u.shape == (7, 11)
+        assert np.allclose(np.asarray(u), np.asarray(v), rtol=16*np.finfo(float).eps)
+
+    @m.integrate
+    def f_process(t, x=0, y=0, z=0, w=0):
+        return ({'dt': 1, 'dw': 1}, {'dt': 1}, {'dw': 1}, {})
+    xs = f_process(x0=(1,)*4, paths=11, steps=30)(t)
+    assert np.allclose(np.asarray(xs[1])[-1], 2.) and np.array_equal(np.asarray(xs[3])[-1], np.ones(11))

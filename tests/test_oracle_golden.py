@@ -45,6 +45,16 @@ def test_user_system_replay_bit_exact(name, addaxis):
     assert np.array_equal(x, g['out0']) and np.array_equal(y, g['out1'])
 
 
+def test_user_system_with_jumps_replay_bit_exact():
+    """'dt' + 'dn' + 'dw' terms, time-dependent coefficient (sorted-id sum)."""
+    from tests.cases import jump_system, k_of_t
+    g = golden('replay_system_jumps')
+    where = np.searchsorted(g['grid'], g['tt'])
+    x, y = orc.system_replay(jump_system, 2, dict(k=k_of_t), (1., .5), g['grid'], where,
+                             g['dW'], True, dN=g['dN'])
+    assert np.array_equal(x, g['out0']) and np.array_equal(y, g['out1'])
+
+
 def test_step_grid_matches_reference_merge():
     for name in sorted(REPLAY):
         g = golden(name)
