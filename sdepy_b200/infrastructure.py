@@ -1008,12 +1008,46 @@ class cpoisson_source(source):
 
     def __call__(self, t, dt):
         if not self.device_ready():
-            raise NotImplementedError(
-                'cpoisson_source with a custom dn source or a non-preset jump '
-                'law has no device implementation')
+            return self._call_with_user_objects(t, dt)
         dj, dn = _draw_cpoisson(self, self.dn, self.y, t, dt, want_dj=True)
         self.dn_value = dn
         return dj
+
+    def _call_with_user_objects(self, t, dt):
+        """A user-supplied ``dn`` source or jump-size object (anything with an
+        ``rvs(size, random_state)`` method, e.g. a frozen scipy.stats law) is
+        Python code and is evaluated where it lives, on the host, with the
+        reference's protocol (infrastructure.py:2002-2040): counts from
+        ``self.dn`` (the device Poisson draw unless it is a user source too),
+        then one ``rvs`` block of shape ``(paths with j jumps, j)`` per count j.
+        An SDE fed by such a source runs through the generic replay path."""
+        t, dt = np.broadcast_arrays(t, dt)
+        if t.shape != ():
+            raise NotImplementedError('array-valued t, dt')
+        sign = int(np.sign(dt))
+        dn = np.asarray(self.dn(t, dt))
+        counts = sign*dn
+        rv = self.y(float(t) + float(dt)/2) if callable(self.y) else self.y
+        dz = np.zeros(self.vshape + (self.paths,), dtype=float if self.dtype is None else self.dtype)
+        y_value = []
+        for j in range(1, int(counts.max(initial=0)) + 1):
+            index = counts == j
+            if index.any():
+                size = (int(index.sum()), j)
+                try:
+                    sample = rv.rvs(size=size, random_state=self._rng)
+                except TypeError:
+                    import warnings
+                    sample = rv.rvs(size=size)
+                    warnings.warn(
+                        'The use of cpoission_source with distributions not '
+                        'accepting a `random_state` keyword argument is '
+                        'deprecated, and will not be supported in future '
+                        'releases.', DeprecationWarning)
+                dz[index] = sign*np.asarray(sample).sum(axis=-1)
+                y_value.append(sample)
+        self.dn_value, self.y_value = dn, y_value
+        return dz
 
 
 def lane_values(z, lead_shape, what='parameter', paths=None):

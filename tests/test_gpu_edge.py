@@ -292,3 +292,43 @@ def test_online_statistics_every_row_and_groups():
     # too many rows x components for the in-kernel accumulators: loud failure
     with pytest.raises(NotImplementedError):
         m.wiener_process(paths=10, vshape=(40,), output='stats')(np.linspace(0, 1, 400))
+
+
+def test_cpoisson_with_user_jump_size_objects():
+    """The reference's protocol for user jump-size laws (tests/test_source.py:
+    257-284): any object with ``rvs(size, random_state)``; with a constant law
+    ``dj == dn*val``.  Counts are drawn on the device, the user's Python
+    object is evaluated on the host; an SDE driven by it runs through the
+    generic replay path and keeps ``jump_count`` consistent."""
+    import scipy.stats
+    import sdepy_b200 as m
+    val = 2.
+
+    class const_rv:
+        def rvs(self, size, random_state):
+            return np.full(size, fill_value=val)
+
+    class const_rv_legacy:
+        def rvs(self, size):
+            return np.full(size, fill_value=val)
+
+    src = m.cpoisson_source(lam=1., paths=100, ptype=np.int16, y=const_rv(), seed=3)
+    for dt in (1, 100, -2):
+        s, n = src(0, dt), src.dn_value
+        assert s.shape == (100,) and np.array_equal(n*val, s)
+    assert (src(0, -2) <= 0).all()
+    src = m.cpoisson_source(lam=1., paths=100, y=const_rv_legacy(), seed=4)
+    with pytest.warns(DeprecationWarning):
+        s, n = src(0, 1), src.dn_value
+    assert np.array_equal(n*val, s)
+
+    # a frozen scipy law inside a jump-diffusion: log x jumps by N(-.1, .15)
+    P = m.jumpdiff_process(x0=1., mu=.05, sigma=.2, lam=20., y=scipy.stats.norm(-.1, .15),
+                           paths=4000, steps=50, seed=6, rng=np.random.default_rng(1))
+    x = P((0., 1.))
+    assert x.shape == (2, 4000) and np.isfinite(x).all()
+    assert abs(P.info['jump_count'].mean() - 20.) < 4*np.sqrt(20./4000)
+    want = np.exp(.05 - .02 + 20.*(np.exp(-.1 + .15**2/2) - 1))     # E[x(1)]
+    sd_log = np.sqrt(.04 + 20.*(.1**2 + .15**2))
+    assert abs(np.log(x[-1]).mean() - (.05 - .02 + 20.*(-.1))) < 4*sd_log/np.sqrt(4000)
+    assert want > 0
