@@ -17,7 +17,7 @@ default --, 'device' HBM-resident container, 'stats' fused statistics only),
 import numpy as np
 import torch
 
-from . import _engine, _jit, _lib
+from . import _cuda, _engine, _jit, _lib
 from .infrastructure import (
     process, device_process, wiener_source, poisson_source, cpoisson_source,
     odd_wiener_source, even_cpoisson_source, even_poisson_source,
@@ -676,7 +676,7 @@ class SDE(_jit._traced):
         xx = self._from_lanes(res.out.reshape((tt.size, -1, self.paths)),
                               (self.paths,))
         if self.output == 'process':
-            xx = xx.cpu().numpy()
+            xx = _cuda.to_host(xx)
         return xx
 
     # layout hooks: the kernel wants the components of one lane adjacent

@@ -117,6 +117,19 @@ def main():
                                             output='device')((0., 1.)))
     rec('replay lognorm terminal only', p, n, t, stored=2*p, read=p*n)
     del x
+    # the drop-in default: host `process` result (pinned D2H of the 4 GB slab included)
+    p_, n_ = int(1_000_000*a.scale), 500
+    tl_ = np.linspace(0., 5., n_ + 1)
+    run = lambda: sd.ornstein_uhlenbeck_process(
+        x0=.1, theta=.2, k=1., sigma=.3, paths=p_, seed=2)(tl_)
+    run()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter(); xh = run(); ts.append(time.perf_counter() - t0)
+    res.append(dict(config="OU full path to a host process (output='process', default)",
+                    paths=p_, steps=n_, seconds_wall=min(ts),
+                    path_steps_per_s_wall=p_*n_/min(ts), d2h_GBps=8.*p_*(n_ + 1)/min(ts)/1e9))
+    del xh
     # non-log model: no exp at the store, pure stream (read 8 B + write 8 B per path-step)
     t, x = timed(lambda: sd.ornstein_uhlenbeck_process(
         x0=.1, theta=.2, k=1., sigma=.3, paths=p, dw=sd.replay_source(dW),
