@@ -20,3 +20,11 @@ for r in rows:
     if 'GBps' in r:
         print('| %s | %.5f | %.0f | %.2f |' % (r['config'], r['seconds'], r['GBps'],
                                              r['frac_of_copy_peak']))
+print()
+print('| host-facing run | paths × steps | wall s | path-steps/s (wall) | D2H GB/s (whole call) |')
+print('|---|---|---|---|---|')
+for r in rows:
+    if 'seconds_wall' in r:
+        print('| %s | %.0e × %d | %.4f | %.3e | %.1f |' % (
+            r['config'], r['paths'], r['steps'], r['seconds_wall'],
+            r['path_steps_per_s_wall'], r['d2h_GBps']))
