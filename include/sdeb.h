@@ -87,7 +87,17 @@ typedef struct sdeb_problem {
     int64_t params_per_path;  /* records carry a trailing path axis:
                                  params[n_psteps][n_groups][npt][pitch] (parameters that
                                  vary along the paths axis, e.g. process-valued ones) */
-    uint64_t seed;            /* Philox key                                     */
+    uint64_t seed;            /* Philox4x32-10 key.  Counter = (global path low 32
+                                 bits, path bits 32..39 | group << 8, step word,
+                                 stream | component << 16).  Normals: step word =
+                                 n / P with P in {1, 2, 4} the number of steps that
+                                 consume whole blocks (a block = two Box-Muller pairs
+                                 of 64 bits), stream = block index; Poisson counts:
+                                 step word = even step, stream 0x100; jump sizes:
+                                 stream 0x200 + j; exponent extension of a pair
+                                 (probability 2^-12): stream 0x8000 + pair.  Results
+                                 depend on (seed, global path, group) only -- not on
+                                 the sharding, the grid or the launch geometry     */
     const double* steps;      /* [n_steps][2]: dt = t[n+1]-t[n] (integration.py:714),
                                  sqrt|dt| (infrastructure.py:1558-1559)         */
     const int32_t* store_row; /* [n_steps]: row storing the state after step n
