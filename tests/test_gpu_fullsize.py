@@ -121,3 +121,32 @@ def test_config5_milstein_1e8_montecarlo():
     one = m.montecarlo(x.x[-1], bins=edges)
     assert np.array_equal(one.histogram()[0], counts)
     assert np.allclose(one.mean(), a.mean(), rtol=1e-12)
+
+
+def test_long_timeline_few_paths_is_exact():
+    """The other extreme the reference talks about ("one million time steps
+    across 100 paths", sdepy/__init__.py:87-91): 300 000 steps of 100 paths,
+    every step stored.  The Wiener Euler scheme is a running sum, so the
+    dumped increments replayed on the host (same operation order) must give
+    the stored paths bit for bit -- step staging, store rows and the Philox
+    period addressing over a long run."""
+    m = sd()
+    n, paths = 300_000, 100
+    tt = np.linspace(0., 3., n + 1)
+    P = m.wiener_process(x0=1., mu=.3, sigma=.7, paths=paths, seed=5)
+    P._dump_increments = True
+    x = P(tt)
+    assert x.shape == (n + 1, paths) and np.isfinite(x).all()
+    dW = P._last_run.dump[0]['dW'].cpu().numpy()[:, 0]          # [n, paths]
+    ds = np.diff(tt)
+    want = np.empty((n + 1, paths))
+    want[0] = 1.
+    acc = want[0].copy()
+    for k in range(n):
+        acc = acc + (.3*ds[k] + .7*dW[k])
+        want[k + 1] = acc
+    assert np.array_equal(np.asarray(x), want)
+    # and the increments are N(0, dt) along the whole run
+    z = dW/np.sqrt(ds)[:, None]
+    assert abs(z.mean()) < 4/np.sqrt(z.size) and abs(z.var() - 1) < 4*np.sqrt(2/z.size)
+    assert abs(np.mean(z[:-1]*z[1:])) < 4/np.sqrt(z.size)       # no lag-1 correlation
