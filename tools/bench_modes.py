@@ -12,7 +12,10 @@ import time
 import numpy as np
 import torch
 
-import sdepy_b200 as sd
+import os as _os
+import sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+import sdepy_b200 as sd  # noqa: E402
 
 HBM_GBS = 6553.6      # MEASURED_PEAKS.json (copy bandwidth, read+write)
 

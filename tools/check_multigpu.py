@@ -10,7 +10,10 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-import sdepy_b200 as sd
+import os as _os
+import sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+import sdepy_b200 as sd  # noqa: E402
 from sdepy_b200.distributed import shard
 
 

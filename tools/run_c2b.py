@@ -2,7 +2,10 @@
 import sys
 import numpy as np
 import torch
-import sdepy_b200 as sd
+import os as _os
+import sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+import sdepy_b200 as sd  # noqa: E402
 
 
 def hw_theta(t):
