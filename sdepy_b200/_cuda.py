@@ -57,6 +57,48 @@ def to_host(t):
     return h.numpy()
 
 
+class device_array(torch.Tensor):
+    """CUDA tensor handed out by device-resident sources: still a tensor for
+    the kernels (no copy when it is fed back as ``dw=``), and an array for NumPy
+    (``np.asarray``, ``assert_array_equal``, arithmetic with ndarrays pull a
+    host copy), so that code written against the reference's ndarray-returning
+    sources keeps working."""
+
+    def __array__(self, dtype=None, copy=None):
+        a = to_host(self.detach().as_subclass(torch.Tensor))
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kw):
+        """NumPy ufuncs (``np.exp(z)``, ``ndarray * z``) work on host copies
+        and return ndarrays."""
+        args = [np.asarray(a) if isinstance(a, device_array) else a for a in inputs]
+        return getattr(ufunc, method)(*args, **kw)
+
+
+def _mixed(name):
+    """Binary operator that stays on the device for scalars and tensors and
+    hands ndarray operands to NumPy."""
+    base = getattr(torch.Tensor, name)
+
+    def op(self, other):
+        if isinstance(other, np.ndarray):
+            return getattr(np.asarray(self), name)(other)
+        return base(self, other)
+    op.__name__ = name
+    return op
+
+
+for _name in ('__add__', '__radd__', '__sub__', '__rsub__', '__mul__', '__rmul__',
+              '__truediv__', '__rtruediv__', '__pow__', '__eq__', '__ne__',
+              '__lt__', '__le__', '__gt__', '__ge__'):
+    setattr(device_array, _name, _mixed(_name))
+device_array.__hash__ = torch.Tensor.__hash__
+
+
+def as_device_array(t):
+    return t.as_subclass(device_array)
+
+
 def ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 

@@ -218,20 +218,47 @@ class process(np.ndarray):
         t = getattr(obj, 't', None)
         self.t = t if (t is not None and t.shape == self.shape[:1]) else None
 
+    def _is_compatible(self, other):
+        """Two processes broadcast only if they share the timeline (or one is
+        constant) and their values and paths broadcast axis by axis, vshapes
+        of equal length (reference infrastructure.py:458-471)."""
+        t_ok = (self.t.size == 1 or other.t.size == 1
+                or np.array_equal(self.t, other.t))
+        s1, s2 = self.shape[1:], other.shape[1:]
+        return t_ok and len(s1) == len(s2) and all(
+            a == b or a == 1 or b == 1 for a, b in zip(s1, s2))
+
     def __array_wrap__(self, out, context=None, return_scalar=False):
         """ufunc results stay processes, on the common non-constant timeline of
-        the process operands (reference infrastructure.py:505-540); ndarray
-        methods (sum, mean ...) return plain arrays."""
+        the process operands, else the constant timeline of the first one;
+        incompatible process operands raise ValueError (reference
+        infrastructure.py:486-540: its __array_prepare__ check, which NumPy 2
+        no longer calls, is made here); ndarray methods (sum, mean ...) return
+        plain arrays."""
         if context is None:
             return np.asarray(out)
-        t = None
-        for a in context[1]:
-            ta = getattr(a, 't', None) if isinstance(a, process) else None
-            if ta is not None and ta.shape == out.shape[:1] and (t is None or t.size == 1):
-                t = ta
-        if t is None:
-            return np.asarray(out)
-        res = np.asarray(out).view(type(self))
+        procs = [a for a in context[1] if isinstance(a, process)]
+        for a in procs:
+            if getattr(a, 't', None) is None:
+                raise ValueError(
+                    'cannot operate on a process without a timeline. '
+                    'if this results from array operations on processes, '
+                    'try using their array views instead (x attribute)')
+        for a in procs:
+            if not a._is_compatible(self):
+                raise ValueError(
+                    'processes could not be broadcast together due to '
+                    'incompatible shapes {}, {} and/or timelines'
+                    .format(a.shape, self.shape))
+        t = procs[0].t if procs else self.t
+        for a in procs[1:]:
+            if a.t.size > 1:
+                t = a.t
+                break
+        out = np.asarray(out)
+        if t is None or t.shape != out.shape[:1]:
+            return out
+        res = out.view(type(self))
         res.t = t
         return res
 
@@ -331,6 +358,8 @@ class process(np.ndarray):
         return f(s + np.asarray(ds)) - f(s)
 
     def _summary(self, name, **kw):
+        if 'dtype' in kw and kw['dtype'] is None:
+            kw['dtype'] = self.dtype       # reference 851-889: accumulate in own dtype
         return process(t=self.t, x=getattr(self.x, name)(axis=-1, keepdims=True, **kw))
 
     def _at(self, t):
@@ -366,23 +395,23 @@ class process(np.ndarray):
         yy = y.reshape(t.shape + (1,)*x.ndim + y.shape[t.ndim:])
         return (yy <= xx).sum(axis=-1)/self.paths
 
-    def psum(self):
-        return self._summary('sum')
+    def psum(self, dtype=None, out=None):
+        return self._summary('sum', dtype=dtype, out=out)
 
-    def pmean(self):
-        return self._summary('mean')
+    def pmean(self, dtype=None, out=None):
+        return self._summary('mean', dtype=dtype, out=out)
 
-    def pvar(self, ddof=0):
-        return self._summary('var', ddof=ddof)
+    def pvar(self, dtype=None, out=None, ddof=0):
+        return self._summary('var', dtype=dtype, out=out, ddof=ddof)
 
-    def pstd(self, ddof=0):
-        return self._summary('std', ddof=ddof)
+    def pstd(self, dtype=None, out=None, ddof=0):
+        return self._summary('std', dtype=dtype, out=out, ddof=ddof)
 
-    def pmin(self):
-        return self._summary('min')
+    def pmin(self, out=None):
+        return self._summary('min', out=out)
 
-    def pmax(self):
-        return self._summary('max')
+    def pmax(self, out=None):
+        return self._summary('max', out=out)
 
     # ---- timeline helpers, summaries across values and along time ---------
     # (reference infrastructure.py:731-766, 894-1122)
@@ -407,44 +436,44 @@ class process(np.ndarray):
         return process(t=self.t[:1],
                        x=getattr(np.asarray(self), name)(axis=0, keepdims=True, **kw))
 
-    def vmin(self):
-        return self._vsummary('min')
+    def vmin(self, out=None):
+        return self._vsummary('min', out=out)
 
-    def vmax(self):
-        return self._vsummary('max')
+    def vmax(self, out=None):
+        return self._vsummary('max', out=out)
 
-    def vsum(self):
-        return self._vsummary('sum')
+    def vsum(self, dtype=None, out=None):
+        return self._vsummary('sum', dtype=dtype, out=out)
 
-    def vmean(self):
-        return self._vsummary('mean')
+    def vmean(self, dtype=None, out=None):
+        return self._vsummary('mean', dtype=dtype, out=out)
 
-    def vvar(self, ddof=0):
-        return self._vsummary('var', ddof=ddof)
+    def vvar(self, dtype=None, out=None, ddof=0):
+        return self._vsummary('var', dtype=dtype, out=out, ddof=ddof)
 
-    def vstd(self, ddof=0):
-        return self._vsummary('std', ddof=ddof)
+    def vstd(self, dtype=None, out=None, ddof=0):
+        return self._vsummary('std', dtype=dtype, out=out, ddof=ddof)
 
-    def tmin(self):
-        return self._tsummary('min')
+    def tmin(self, out=None):
+        return self._tsummary('min', out=out)
 
-    def tmax(self):
-        return self._tsummary('max')
+    def tmax(self, out=None):
+        return self._tsummary('max', out=out)
 
-    def tsum(self):
-        return self._tsummary('sum')
+    def tsum(self, dtype=None, out=None):
+        return self._tsummary('sum', dtype=dtype, out=out)
 
-    def tmean(self):
-        return self._tsummary('mean')
+    def tmean(self, dtype=None, out=None):
+        return self._tsummary('mean', dtype=dtype, out=out)
 
-    def tvar(self, ddof=0):
-        return self._tsummary('var', ddof=ddof)
+    def tvar(self, dtype=None, out=None, ddof=0):
+        return self._tsummary('var', dtype=dtype, out=out, ddof=ddof)
 
-    def tstd(self, ddof=0):
-        return self._tsummary('std', ddof=ddof)
+    def tstd(self, dtype=None, out=None, ddof=0):
+        return self._tsummary('std', dtype=dtype, out=out, ddof=ddof)
 
-    def tcumsum(self):
-        return process(t=self.t, x=np.asarray(self).cumsum(axis=0))
+    def tcumsum(self, dtype=None, out=None):
+        return process(t=self.t, x=np.asarray(self).cumsum(axis=0, dtype=dtype, out=out))
 
     def tdiff(self, dt_exp=0, fwd=True):
         """``q[i] = (p[i+1] - p[i])/(t[i+1] - t[i])**dt_exp`` at ``t[i]``
@@ -936,6 +965,27 @@ class _law:
             raise ValueError('domain error in arguments')
         return self.kind, a, b, pa
 
+    def rvs(self, size, random_state=None):
+        """Host-side variates with the ``scipy.stats`` ``rvs`` signature: the
+        protocol through which foreign consumers (e.g. the reference's own
+        list-based ``true_cpoisson_source``) draw jump sizes.  The device path
+        never calls it: in-kernel draws come from ``jump_size`` (csrc)."""
+        if any(callable(z) for z in self.params.values()):
+            raise TypeError('time-dependent distribution: evaluate it at a '
+                            'time first, y(t).rvs(size)')
+        _, a, b, pa = self.at(0.)
+        rng = (random_state if hasattr(random_state, 'standard_normal')
+               else np.random.default_rng(random_state))
+        if self.kind == _lib.LAW_NORMAL:
+            return a + b*rng.standard_normal(size)
+        if self.kind == _lib.LAW_UNIFORM:
+            return a + (b - a)*rng.random(size)
+        if self.kind == _lib.LAW_EXP:
+            return a*rng.standard_exponential(size)
+        plus = a*rng.standard_exponential(size)
+        minus = b*rng.standard_exponential(size)
+        return np.where(rng.random(size) <= pa, plus, -minus) + 0
+
     # moments used by analytical formulae (reference 1719, 1727, 1743-1791)
     def _const(self):
         return self.at(0.)[1:]
@@ -966,26 +1016,63 @@ class _law:
         return (pa/(1 - a) if a < 1 else np.inf) + (1 - pa)/(1 + b) + 0
 
 
+class _timed_law(_law):
+    """A law with callable parameters is itself a callable ``y(t)`` returning
+    the law frozen at ``t``, like the reference's time-dependent distributions
+    (infrastructure.py:1640-1650)."""
+
+    def __call__(self, t):
+        _, a, b, pa = self.at(t)
+        return _law(self.kind, a=a, b=b, pa=pa)
+
+
+def _make_law(kind, **params):
+    timed = any(callable(z) for z in params.values())
+    return (_timed_law if timed else _law)(kind, **params)
+
+
 def norm_rv(a=0, b=1):
     """Normal jump sizes, mean ``a`` and standard deviation ``b``
     (reference infrastructure.py:1653-1664)."""
-    return _law(_lib.LAW_NORMAL, a=a, b=b)
+    return _make_law(_lib.LAW_NORMAL, a=a, b=b)
 
 
 def uniform_rv(a=0, b=1):
     """Uniform jump sizes in [a, b] (reference 1667-1677)."""
-    return _law(_lib.LAW_UNIFORM, a=a, b=b)
+    return _make_law(_lib.LAW_UNIFORM, a=a, b=b)
 
 
 def exp_rv(a=1):
     """Exponential jump sizes with (signed) scale ``a`` (reference 1680-1693)."""
-    return _law(_lib.LAW_EXP, a=a)
+    return _make_law(_lib.LAW_EXP, a=a)
 
 
 def double_exp_rv(a=1, b=1, pa=0.5):
     """Double exponential: scale ``a`` with probability ``pa``, ``-b``
     otherwise (reference 1696-1712)."""
-    return _law(_lib.LAW_DOUBLE_EXP, a=a, b=b, pa=pa)
+    return _make_law(_lib.LAW_DOUBLE_EXP, a=a, b=b, pa=pa)
+
+
+def rvmap(f, y):
+    """Distribution of ``f(y)`` -- or of ``f(t, y(t))`` when ``f``'s first
+    argument is named ``t`` or ``s`` and/or ``y`` is time-dependent -- as an
+    object with an ``rvs(size, random_state=None)`` method, or a callable of
+    ``t`` returning one, as accepted by ``cpoisson_source`` (reference
+    infrastructure.py:1799-1862).  Like any user-supplied ``rvs`` object it is
+    evaluated on the host over device-drawn counts."""
+    timed = _signature(f)[0][0] in ('t', 's')
+
+    class mapped:
+        def __init__(self, rv, t=None):
+            self._rv, self._t = rv, t
+
+        def rvs(self, size, random_state=None):
+            z = self._rv.rvs(size=size, random_state=random_state)
+            return f(self._t, z) if timed else f(z)
+
+    if callable(y) or timed:
+        return lambda t: mapped(y(t) if callable(y) else y, t)
+    return mapped(y)
 
 
 class cpoisson_source(source):
@@ -1132,9 +1219,9 @@ class odd_wiener_source(wiener_source):
     In-kernel the second half reuses the Philox stream of path p - K."""
     antithetic = True
 
-    def __init__(self, *, paths=2, **kw):
+    def __init__(self, *, paths=2, vshape=(), dtype=None, rng=None, **args):
         _check_even(paths)
-        super().__init__(paths=paths, **kw)
+        super().__init__(paths=paths, vshape=vshape, dtype=dtype, rng=rng, **args)
 
     def __call__(self, t, dt):
         self.paths //= 2
@@ -1150,9 +1237,9 @@ class even_poisson_source(poisson_source):
     infrastructure.py:2113-2130)."""
     antithetic = True
 
-    def __init__(self, *, paths=2, **kw):
+    def __init__(self, *, paths=2, vshape=(), dtype=None, rng=None, **args):
         _check_even(paths)
-        super().__init__(paths=paths, **kw)
+        super().__init__(paths=paths, vshape=vshape, dtype=dtype, rng=rng, **args)
 
     def __call__(self, t, dt):
         self.paths //= 2
@@ -1169,9 +1256,9 @@ class even_cpoisson_source(cpoisson_source):
     expose ``dn_value``."""
     antithetic = True
 
-    def __init__(self, *, paths=2, **kw):
+    def __init__(self, *, paths=2, vshape=(), dtype=None, rng=None, **args):
         _check_even(paths)
-        super().__init__(paths=paths, **kw)
+        super().__init__(paths=paths, vshape=vshape, dtype=dtype, rng=rng, **args)
 
     def __call__(self, t, dt):
         self.paths //= 2
@@ -1285,8 +1372,8 @@ class true_wiener_source(source):
     def _values(self, s):
         s = np.asarray(s, dtype=float)
         rows = [self._value(float(v)) for v in s.reshape(-1)]
-        out = torch.stack(rows) if rows else None
-        return out.reshape(s.shape + self.vshape + (self.paths,))
+        out = torch.stack(rows) if rows else _cuda.empty((0,), _cuda.device(self._device))
+        return _cuda.as_device_array(out.reshape(s.shape + self.vshape + (self.paths,)))
 
     def __call__(self, t, dt=None):
         if dt is None:
@@ -1424,19 +1511,95 @@ class montecarlo:
         self._mean[...] = (n*self._mean + m*smean)/(n + m)
         if self._bins is not None:
             if first:
-                self._setup_bins(vshape, lo, hi)
+                self._setup_bins(vshape, lo, hi, rows=rows, m=m, centred=st,
+                                 integer=np.issubdtype(
+                                     getattr(sample, 'dtype', np.dtype(float))
+                                     if isinstance(sample, np.ndarray) else float,
+                                     np.integer))
             self._update_histogram(rows, m)
         self._paths[0] += m
 
-    def _setup_bins(self, vshape, lo, hi):
+    @staticmethod
+    def _bin_width(name, row, n, a, b, mom, integer):
+        """Bin width of numpy.histogram_bin_edges' named estimators
+        (numpy/lib/_histograms_impl.py) for one component of the first sample,
+        from device-side statistics: ``mom`` = centred power sums S1..S4 of the
+        sdeb_moments pass, quartiles from a device sort (one-off setup work;
+        the counting itself is the histogram kernel)."""
+        ptp = b - a
+        var = mom[1]/n - (mom[0]/n)**2
+        std = np.sqrt(max(var, 0.))
+
+        def sturges():
+            return ptp/(np.log2(n) + 1.0)
+
+        def fd():
+            srt = torch.sort(row).values
+            q = []
+            for frac in (.75, .25):               # np.percentile, linear interpolation
+                pos = frac*(n - 1)
+                k = int(np.floor(pos))
+                lo_v, hi_v = (float(srt[k]), float(srt[min(k + 1, n - 1)]))
+                q.append(lo_v + (hi_v - lo_v)*(pos - k))
+            return 2.0*(q[0] - q[1])*n**(-1.0/3.0)
+
+        if name == 'auto':
+            w = fd()
+            w = min(w, sturges()) if w else sturges()
+        elif name == 'fd':
+            w = fd()
+        elif name == 'sturges':
+            w = sturges()
+        elif name == 'sqrt':
+            w = ptp/np.sqrt(n)
+        elif name == 'rice':
+            w = ptp/(2.0*n**(1.0/3))
+        elif name == 'scott':
+            w = (24.0*np.pi**0.5/n)**(1.0/3.0)*std
+        elif name == 'doane':
+            w = 0.0
+            if n > 2:
+                sg1 = np.sqrt(6.0*(n - 2)/((n + 1.0)*(n + 3)))
+                if std > 0.0:
+                    mu = mom[0]/n
+                    m3 = mom[2]/n - 3*mu*mom[1]/n + 2*mu**3
+                    g1 = m3/std**3
+                    w = ptp/(1.0 + np.log2(n) + np.log2(1.0 + np.absolute(g1)/sg1))
+        else:
+            raise ValueError('{!r} is not a valid estimator for `bins`'.format(name)
+                             if name != 'stone' else
+                             "the 'stone' estimator is not available on the device")
+        if integer and w and w < 1:
+            w = 1
+        return w
+
+    def _setup_bins(self, vshape, lo, hi, rows=None, m=0, centred=None, integer=False):
         bins = self._bins
         nrow = int(np.prod(vshape, dtype=int))
         self._edges, self._uniform = [], []
         if isinstance(bins, str):
-            raise NotImplementedError(
-                'data-driven bin estimators ({!r}) are not available on the '
-                'device: pass an integer or explicit edges'.format(bins))
-        if isinstance(bins, (int, np.integer)):
+            for i in range(nrow):
+                if self._range is not None:
+                    a, b = map(float, self._range)
+                    if a > b:
+                        raise ValueError('max must be larger than min in range parameter.')
+                    if (a, b) != (float(lo[i]), float(hi[i])):
+                        raise NotImplementedError(
+                            'named bin estimators with an explicit range are not '
+                            'available on the device')
+                else:
+                    a, b = float(lo[i]), float(hi[i])
+                if not (np.isfinite(a) and np.isfinite(b)):
+                    raise ValueError('autodetected range of [{}, {}] is not finite'.format(a, b))
+                if a == b:
+                    a, b = a - 0.5, b + 0.5
+                    nb = 1
+                else:
+                    w = self._bin_width(bins, rows[i], m, a, b, centred[i], integer)
+                    nb = int(np.ceil((b - a)/w)) if w else 1
+                self._edges.append(np.linspace(a, b, nb + 1))
+                self._uniform.append(True)
+        elif isinstance(bins, (int, np.integer)):
             for i in range(nrow):
                 if self._range is not None:
                     a, b = map(float, self._range)
