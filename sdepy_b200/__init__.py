@@ -10,7 +10,8 @@ from . import _lib                                   # fails loudly if the .so i
 from .infrastructure import (                        # noqa: F401
     process, piecewise, device_process, montecarlo,
     source, wiener_source, poisson_source, cpoisson_source, replay_source,
-    odd_wiener_source, even_poisson_source, even_cpoisson_source, true_wiener_source,
+    odd_wiener_source, even_poisson_source, even_cpoisson_source,
+    true_source, true_wiener_source,
     norm_rv, uniform_rv, exp_rv, double_exp_rv, rvmap)
 from .integration import (                           # noqa: F401
     paths_generator, integrator, SDE, SDEs, integrate, path_stats,

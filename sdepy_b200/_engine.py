@@ -148,7 +148,9 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
         p = _lib.Problem()
         p.abi_version = _lib.ABI_VERSION
         p.model, p.ncomp, p.jit_handle = spec.model, spec.ncomp, spec.jit_handle
-        p.noise = _lib.NOISE_REPLAY if replay is not None else _lib.NOISE_PHILOX
+        # a sweep without steps (single-point timeline) draws nothing
+        use_replay = replay is not None and n > 0
+        p.noise = _lib.NOISE_REPLAY if use_replay else _lib.NOISE_PHILOX
         p.n_paths, p.path_offset, p.pitch = paths, path_offset, paths
         p.n_steps, p.n_groups, p.n_rows = n, spec.groups, n_rows
         p.row0 = seg.row0 if k == 0 else -1
@@ -166,7 +168,7 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
         if not per_path:
             p.params_host = rec.ctypes.data      # rec stays alive in `keep`
         keep.append(rec)
-        if replay is not None:
+        if use_replay:
             tabs = replay[k]
             for name in ('dW', 'dJ', 'dN'):
                 t = tabs.get(name)

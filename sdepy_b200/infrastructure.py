@@ -894,9 +894,9 @@ class wiener_source(source):
     def __call__(self, t, dt):
         t, dt = np.broadcast_arrays(t, dt)
         if t.shape != ():
-            out = np.empty(t.shape + self.vshape + (self.paths,))
+            out = np.empty(t.shape + self.vshape + (self.paths,), dtype=self.dtype)
             for i in np.ndindex(t.shape):
-                out[i] = self(t[i], dt[i])
+                out[i] = wiener_source.__call__(self, t[i], dt[i])
             return out
         dev = _cuda.device()
         vs = self.vshape
@@ -915,7 +915,25 @@ class wiener_source(source):
                 _cuda.ptr(out), groups, ndw, self.paths, self.paths, 0,
                 self.next_key(), 0, float(np.sqrt(np.abs(dt))),
                 _cuda.ptr(chol), _cuda.stream_ptr(dev)))
-        return out.cpu().numpy().reshape(vs + (self.paths,))
+        return out.cpu().numpy().reshape(vs + (self.paths,)).astype(self.dtype, copy=False)
+
+
+def _over_times(src, call, t, dt, shape, dtype, extras=()):
+    """Source call vectorised over array-valued ``t, dt`` (output shaped
+    ``t.shape + vshape + (paths,)``, reference infrastructure.py:1321-1330);
+    ``extras`` names attributes (``dn_value`` ...) stacked the same way."""
+    t, dt = np.broadcast_arrays(t, dt)
+    out = np.empty(t.shape + shape, dtype=dtype)
+    side = {k: [] for k in extras}
+    for i in np.ndindex(t.shape):
+        out[i] = call(src, t[i], dt[i])
+        for k in extras:
+            if hasattr(src, k):
+                side[k].append(getattr(src, k))
+    for k, v in side.items():
+        if v and k != 'y_value':
+            setattr(src, k, np.stack(v).reshape(t.shape + np.shape(v[0])))
+    return out
 
 
 class poisson_source(source):
@@ -941,6 +959,9 @@ class poisson_source(source):
                           dtype=float)
 
     def __call__(self, t, dt):
+        if np.ndim(t) or np.ndim(dt):
+            return _over_times(self, poisson_source.__call__, t, dt,
+                               self.vshape + (self.paths,), self.dtype)
         dj, dn = _draw_cpoisson(self, self, None, t, dt, want_dj=False)
         return dn
 
@@ -1094,11 +1115,15 @@ class cpoisson_source(source):
         return type(self.dn) is poisson_source and isinstance(self.y, _law)
 
     def __call__(self, t, dt):
+        if np.ndim(t) or np.ndim(dt):
+            return _over_times(self, cpoisson_source.__call__, t, dt,
+                               self.vshape + (self.paths,), self.dtype,
+                               extras=('dn_value', 'y_value'))
         if not self.device_ready():
             return self._call_with_user_objects(t, dt)
         dj, dn = _draw_cpoisson(self, self.dn, self.y, t, dt, want_dj=True)
         self.dn_value = dn
-        return dj
+        return dj.astype(self.dtype, copy=False)
 
     def _call_with_user_objects(self, t, dt):
         """A user-supplied ``dn`` source or jump-size object (anything with an
@@ -1272,7 +1297,15 @@ class even_cpoisson_source(cpoisson_source):
         return np.concatenate((z, z), axis=-1)
 
 
-class true_wiener_source(source):
+class true_source(source):
+    """Base class of sources with memory (reference infrastructure.py:
+    2153-2233): ``s(t)`` is the value of the driving process at ``t``,
+    ``s(t, dt)`` its increment, realisations are stored and interpolated /
+    extended consistently on later calls; ``s[index]`` is a sub-source sharing
+    them."""
+
+
+class true_wiener_source(true_source):
     """dw with memory (reference infrastructure.py:2182-2499): ``dw(t)`` is the
     realised value at time ``t`` of a Wiener path with ``dw(t0) = z0``, and
     ``dw(t, dt) = dw(t + dt) - dw(t)``; new values are drawn conditionally on
@@ -1373,13 +1406,27 @@ class true_wiener_source(source):
         s = np.asarray(s, dtype=float)
         rows = [self._value(float(v)) for v in s.reshape(-1)]
         out = torch.stack(rows) if rows else _cuda.empty((0,), _cuda.device(self._device))
-        return _cuda.as_device_array(out.reshape(s.shape + self.vshape + (self.paths,)))
+        return out.reshape(s.shape + self.vshape + (self.paths,))
+
+    def device_call(self, t, dt=None):
+        """``W(t)`` or ``W(t + dt) - W(t)`` as a CUDA tensor (a
+        ``_cuda.device_array``: NumPy functions accept it and pull a host
+        copy): what the integration kernels consume when the source is passed
+        as ``dw=``, without any round trip through the host."""
+        if dt is None:
+            return _cuda.as_device_array(self._values(t))
+        t, dt = np.broadcast_arrays(t, dt)
+        return _cuda.as_device_array(self._values(t + dt) - self._values(t))
 
     def __call__(self, t, dt=None):
-        if dt is None:
-            return self._values(t)
-        t, dt = np.broadcast_arrays(t, dt)
-        return self._values(t + dt) - self._values(t)
+        """Host array, like every source of the reference (the realisations
+        themselves stay in HBM)."""
+        z = self.device_call(t, dt)
+        return _cuda.to_host(z.as_subclass(torch.Tensor)).astype(self.dtype, copy=False)
+
+    def __getitem__(self, index):
+        """Sub-source over some components, sharing this one's realisations."""
+        return _indexed_true_source(self, index)
 
     @property
     def size(self):
@@ -1388,6 +1435,37 @@ class true_wiener_source(source):
     @property
     def t(self):
         return np.array(self._tlist, dtype=float)
+
+
+class _indexed_true_source:
+    """``s[index]``: the components ``index`` (over the ``vshape`` axes, NumPy
+    indexing, ``np.newaxis`` included) of a source with memory, sharing the
+    parent's stored realisations -- evaluating the view at a new time realises
+    ALL components of the parent there (reference infrastructure.py:2235-2252)."""
+
+    def __init__(self, parent, index):
+        self._parent = parent
+        self._index = index if isinstance(index, tuple) else (index,)
+        self.paths, self.dtype = parent.paths, parent.dtype
+        self.vshape = np.empty(parent.vshape + (1,))[self._index].shape[:-1]
+
+    def _pick(self, z, tshape):
+        return z[(slice(None),)*len(tshape) + self._index]
+
+    def __call__(self, t, dt=None):
+        tshape = np.broadcast(t, 0 if dt is None else dt).shape
+        return self._pick(self._parent(t, dt), tshape)
+
+    def device_call(self, t, dt=None):
+        tshape = np.broadcast(t, 0 if dt is None else dt).shape
+        return self._pick(self._parent.device_call(t, dt), tshape)
+
+    def __getitem__(self, index):
+        return _indexed_true_source(self, index)
+
+    size = property(lambda self: self._parent.size)
+    t = property(lambda self: self._parent.t)
+    rng = property(lambda self: self._parent.rng)
 
 
 class replay_source:
@@ -1473,6 +1551,9 @@ class montecarlo:
             raise ValueError("use must be one of 'all', 'even', 'odd', not {}"
                              .format(self._use))
         x = self._as_device(sample, axis)
+        sdtype = (sample.dtype if isinstance(sample, np.ndarray) else
+                  np.dtype(str(sample.dtype).replace('torch.', ''))
+                  if isinstance(sample, torch.Tensor) else np.dtype(float))
         if self._use != 'all':
             # half-sum / half-difference of antithetic pairs x[k], x[K+k]
             # (reference infrastructure.py:2905-2914)
@@ -1497,7 +1578,9 @@ class montecarlo:
         first = self.paths == 0
         n = self.paths
         if first:
-            dtype = float if self.dtype is None else self.dtype
+            # reference 2928-2930: a floating sample sets the dtype of the results
+            dtype = ((sdtype if sdtype.kind == 'f' else float) if self.dtype is None
+                     else self.dtype)
             self._moments = tuple(np.zeros(vshape, dtype=dtype) for _ in range(4))
             self._mean = np.zeros(vshape, dtype=dtype)
             pass1 = _cuda.moments(rows, m)

@@ -568,14 +568,20 @@ class SDE(_jit._traced):
                         if hasattr(dj, 'dn_value'):
                             rows['dN'].append(self._as_lane_table(dj.dn_value, integer=True))
                     elif id == 'dw':
-                        rows['dW'].append(self._as_lane_table(dw(s, ds)))
+                        # device-resident sources hand over CUDA tensors
+                        call = getattr(dw, 'device_call', dw)
+                        rows['dW'].append(self._as_lane_table(call(s, ds)))
             tab = {}
             for k, v in rows.items():
                 if v:
                     tab[k] = (torch.stack(v) if isinstance(v[0], torch.Tensor)
                               else np.stack(v))
-            if dw is None:
-                tab['dW'] = np.zeros((seg.n_steps,) + self.wshape + (self.paths,))
+            # no Wiener term, or a sweep without steps (single-point timeline)
+            empty = (seg.n_steps,) + self.wshape + (self.paths,)
+            if 'dW' not in tab:
+                tab['dW'] = np.zeros(empty)
+            if dj is not None and 'dJ' not in tab:
+                tab['dJ'] = np.zeros(empty)
             tables.append(tab)
         return tables
 
@@ -639,7 +645,8 @@ class SDE(_jit._traced):
                        for seg in segs]
             self._lowered = (key, (w0l, w0_arg, records))
         if replay is not None:
-            replay = [{k: self._to_lanes(v, 1).reshape((seg.n_steps, -1, self.paths))
+            replay = [{k: self._to_lanes(v, 1).reshape(
+                           (seg.n_steps, -1 if seg.n_steps else 0, self.paths))
                        for k, v in tab.items()} for tab, seg in zip(replay, segs)]
         want_stats = self.output == 'stats'
         centre = self._stats_centre(w0l) if want_stats else None

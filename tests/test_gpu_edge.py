@@ -229,14 +229,14 @@ def test_true_wiener_source_memory_bridge_and_convergence():
     m = sd()
     paths = 100_000
     dw = m.true_wiener_source(paths=paths, vshape=(2,), rho=.5, seed=7)
-    w1 = dw(1.).cpu().numpy()
+    w1 = dw(1.)
     assert w1.shape == (2, paths)
-    assert np.array_equal(dw(1.).cpu().numpy(), w1)               # memory
-    assert np.array_equal(dw(0.).cpu().numpy(), np.zeros((2, paths)))
-    w05 = dw(.5).cpu().numpy()                                    # bridge between 0 and 1
-    w2 = dw(2.).cpu().numpy()                                     # extension
-    w15 = dw(1.5).cpu().numpy()                                   # bridge between 1 and 2
-    assert np.array_equal(dw(.5, 1.).cpu().numpy(), w15 - w05)
+    assert np.array_equal(dw(1.), w1)               # memory
+    assert np.array_equal(dw(0.), np.zeros((2, paths)))
+    w05 = dw(.5)                                    # bridge between 0 and 1
+    w2 = dw(2.)                                     # extension
+    w15 = dw(1.5)                                   # bridge between 1 and 2
+    assert np.array_equal(dw(.5, 1.), w15 - w05)
     assert list(dw.t) == [0., .5, 1., 1.5, 2.] and dw.size == 5*2*paths
     se = 5/np.sqrt(paths)
     for a, ta in ((w05, .5), (w1, 1.), (w15, 1.5), (w2, 2.)):
@@ -249,7 +249,7 @@ def test_true_wiener_source_memory_bridge_and_convergence():
     # time-dependent correlation: matrix bridge keeps unit variances per unit time
     dwt = m.true_wiener_source(paths=paths, vshape=(2,), seed=8,
                                corr=lambda t: np.array(((1., .2 + .3*t), (.2 + .3*t, 1.))))
-    e1, emid = dwt(1.).cpu().numpy(), dwt(.4).cpu().numpy()
+    e1, emid = dwt(1.), dwt(.4)
     assert abs(emid[0].var()/.4 - 1) < 2*se and abs((e1 - emid)[1].var()/.6 - 1) < 2*se
     assert abs(np.corrcoef(emid)[0, 1] - (.2 + .3*.2)) < 2*se
     # convergence study: one Brownian path, nested grids, exact lognormal solution
@@ -259,7 +259,7 @@ def test_true_wiener_source_memory_bridge_and_convergence():
         x = m.lognorm_process(paths=20_000, steps=n + 1, x0=1., mu=.05, sigma=.5, dw=tw)((0., 1.))
         # Euler on log x is exact for constant parameters: identical terminal values
         errs.append(np.asarray(x)[-1])
-    wT = tw(1.).cpu().numpy()
+    wT = tw(1.)
     exact = np.exp((.05 - .125) + .5*wT)
     for e in errs:
         assert np.allclose(e, exact, rtol=1e-12)
