@@ -29,10 +29,12 @@ static int fail(int code, const std::string& msg) {
 #define CUDA_TRY(expr)                                                              \
     do {                                                                            \
         cudaError_t e_ = (expr);                                                    \
-        if (e_ != cudaSuccess)                                                      \
+        if (e_ != cudaSuccess) {                                                    \
+            cudaGetLastError();   /* do not leave it for the next call's check */   \
             return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver \
                             ? SDEB_ENODEV : SDEB_ECUDA,                             \
                         std::string(#expr) + ": " + cudaGetErrorString(e_));        \
+        }                                                                           \
     } while (0)
 
 extern "C" int sdeb_abi_version(void) { return SDEB_ABI_VERSION; }
@@ -92,8 +94,10 @@ static const int64_t kMaxStatsSmem = 96 * 1024;   // accumulators kept in smem u
 static int64_t smem_bytes(const ModelInfo& mi, const sdeb_problem* p, bool stats_in_kernel) {
     int64_t nch = mi.ndw > 1 ? (int64_t)mi.ndw * (mi.ndw + 1) / 2 : 0;
     int64_t npt = mi.npc + nch;
-    // dynamic part only: tables and the staged step block are static __shared__
-    int64_t d = (int64_t)STEP_CHUNK * npt + 8 * NSTAT * mi.nx;
+    // dynamic part only: tables and the staged step block are static __shared__;
+    // parameter records are staged only when time-dependent and shared by the paths
+    const bool staged = p->n_psteps > 1 && !p->params_per_path;
+    int64_t d = (staged ? (int64_t)STEP_CHUNK * npt : 0) + 8 * NSTAT * mi.nx;
     if (stats_in_kernel) d += p->n_rows * p->n_groups * mi.nx * NSTAT;
     int64_t bytes = d * 8;
     if (p->noise == SDEB_NOISE_REPLAY)       // cp.async ring of the replay table
@@ -141,6 +145,13 @@ static int plan_impl(const sdeb_problem* p, sdeb_plan_t* plan, ModelInfo& mi, bo
     plan->stats_in_kernel = (acc <= kMaxStatsSmem) ? 1 : 0;
     bool sik = p->stats != NULL && plan->stats_in_kernel;
     plan->smem_bytes = smem_bytes(mi, p, sik);
+    // 227 KB per CTA on sm_100a, ~10 KB of it static (tables, step block)
+    if (plan->smem_bytes > (227 - 10) * 1024)
+        return fail(SDEB_EINVAL,
+                    "this model does not fit the per-block shared memory (" +
+                    std::to_string(plan->smem_bytes / 1024) + " KB of staged parameter records "
+                    "and replay ring needed, 217 KB available): too many correlated components "
+                    "for time-dependent parameters and/or replayed increments");
     int64_t tiles = ((p->n_paths + kThreads - 1) / kThreads) * p->n_groups;
     int sm = 148, occ = 2;
     int dev = 0;

@@ -153,3 +153,32 @@ def test_montecarlo_named_bins_and_result_dtype(dtype):
         ref_counts, ref_edges = np.histogram(x, bins=name)
         np.testing.assert_allclose(edges, ref_edges, rtol=1e-12)
         np.testing.assert_array_equal(counts, ref_counts)
+
+
+def test_many_component_heston_with_supplied_sources():
+    """reference tests/test_processes.py:216-234: full_heston_process with 3, 5
+    and 10 components, correlated, or driven by a supplied 2N-component source
+    (NVRTC instantiation; the parameter records of time-invariant models are
+    not staged in shared memory, which leaves room for the replay ring)."""
+    m = sd()
+    t = np.linspace(0, 1, 11)
+    rng = np.random.default_rng(0)
+    cm6 = np.eye(6) + .1*rng.random((6, 6))
+    cm6 = (cm6 + cm6.T)/2
+    cases = (
+        dict(vshape=(3,), corr=cm6), dict(vshape=(3,), rho=(.1, .2, .3)),
+        dict(vshape=(5,), dw=m.wiener_source(paths=11, vshape=(10,), seed=1)),
+        dict(vshape=10, dw=m.true_wiener_source(paths=11, vshape=(20,), seed=2)),
+    )
+    for kw in cases:
+        x, y = m.full_heston_process(paths=11, steps=30, **kw)(t)
+        n = kw['vshape'] if isinstance(kw['vshape'], int) else kw['vshape'][0]
+        assert x.shape == y.shape == (11, n, 11)
+        assert np.isfinite(np.asarray(x)).all() and (np.asarray(x) > 0).all()
+    # a failed launch must not poison the next call
+    bad = m.full_heston_process(paths=11, vshape=16, steps=30, theta=lambda t: .04 + t,
+                                dw=m.true_wiener_source(paths=11, vshape=(32,), seed=3))
+    with pytest.raises(Exception):
+        bad(t)
+    x = m.lognorm_process(paths=11, steps=5, seed=1)(t)
+    assert np.isfinite(np.asarray(x)).all()
