@@ -176,8 +176,9 @@ def test_many_component_heston_with_supplied_sources():
         assert x.shape == y.shape == (11, n, 11)
         assert np.isfinite(np.asarray(x)).all() and (np.asarray(x) > 0).all()
     # a failed launch must not poison the next call
-    bad = m.full_heston_process(paths=11, vshape=16, steps=30, theta=lambda t: .04 + t,
-                                dw=m.true_wiener_source(paths=11, vshape=(32,), seed=3))
+    # (20 correlated components, time-dependent records AND a replay ring: 220 KB)
+    bad = m.full_heston_process(paths=11, vshape=10, steps=30, theta=lambda t: .04 + t,
+                                dw=m.true_wiener_source(paths=11, vshape=(20,), seed=3))
     with pytest.raises(Exception):
         bad(t)
     x = m.lognorm_process(paths=11, steps=5, seed=1)(t)
