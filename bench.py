@@ -61,8 +61,11 @@ ALGO_FP64_INSTR_PER_PATH_STEP = 100
 N64_PER_PATH_STEP = 53
 # dram__bytes_read.sum + dram__bytes_write.sum of integrate_lean_kernel<Heston> from the
 # ncu --set full capture in profiles/r01_ncu_integrate_lean_heston.csv (1e7 paths x 252
-# steps per launch: 80 KB + 23 KB -- tables in, per-CTA partial sums out; nothing per path)
-NCU_DRAM_BYTES_PER_LAUNCH = 103156
+# steps per launch): 80.18 MB read + 22.15 MB written = the per-path int64
+# `negative_y_count` diagnostic (getinfo=True, the reference's default: 8 B read per path,
+# 8 B written back, part of it still in L2 when the kernel ends); the tables in and the
+# per-CTA partial sums out are KBs.  10.2 B per path, once per launch -- not per step.
+NCU_DRAM_BYTES_PER_PATH = (80.182528e6 + 22.148864e6)/1e7
 
 
 def parse():
@@ -316,7 +319,7 @@ def run_ours(a):
             'roofline': {
                 'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf,
                 'unit': 'TFLOP/s', 'frac': achieved_tf/peak_tf,
-                'traffic': NCU_DRAM_BYTES_PER_LAUNCH,
+                'traffic': int(NCU_DRAM_BYTES_PER_PATH*paths),
                 'executed': {'fp64_instr_per_path_step': N64_PER_PATH_STEP,
                              'achieved': executed_tf, 'frac': executed_tf/peak_tf},
                 'note': 'per GPU. achieved = ALGORITHMIC work (SURVEY 8d: %d FP64-pipe '
