@@ -313,3 +313,42 @@ def test_device_array_numpy_interop():
         np.testing.assert_allclose(10*np.exp(.2 + .7*z), 10*np.exp(.2 + .7*base))
         assert isinstance(np.arange(3.)*z, np.ndarray) and isinstance(z*np.arange(3.), np.ndarray)
         assert bool((z == base).all()) and bool((z == 3.).any())
+
+
+# ---- rng parameter ------------------------------------------------------------
+
+def test_rng_and_default_rng_reach_every_source():
+    """Same generator state -> same Philox keys, whether the generator is passed
+    as ``rng=`` or installed as ``infrastructure.default_rng`` (reference
+    tests/test_processes.py:556-596, tests/test_source.py:196-226)."""
+    from sdepy_b200 import infrastructure as infra
+
+    def keys(P):
+        return [(k, s.seed, getattr(getattr(s, 'dn', None), 'seed', None))
+                for k, s in sorted(P.sources.items())]
+
+    makers = (
+        lambda rng=None: dict(vshape=2, x0=.1, mu=.2, sigma=.3, lam=.4),
+        lambda rng=None: dict(vshape=(2, 3), dw=sd.wiener_source(paths=11, vshape=(2, 3), rng=rng)),
+        lambda rng=None: dict(vshape=(3,), dw=sd.true_wiener_source(paths=11, vshape=(3,), rng=rng),
+                              dj=sd.cpoisson_source(paths=11, vshape=(3,), rng=rng)),
+        lambda rng=None: dict(vshape=2, dj=sd.poisson_source(paths=11, vshape=2, rng=rng)),
+    )
+    for cls in (sd.jumpdiff_process, sd.kou_jumpdiff_process, sd.mjd):
+        for make in makers:
+            for make_rng in (np.random.default_rng, np.random.RandomState,
+                             lambda z: np.random.Generator(np.random.PCG64(z))):
+                rng1, rng2 = make_rng(1234), make_rng(1234)
+                P1 = cls(**make(rng1), paths=11, rng=rng1)
+                P2 = cls(**make(rng2), paths=11, rng=rng2)
+                assert P1.rng is rng1 and P2.rng is rng2
+                saved = infra.default_rng
+                infra.default_rng = make_rng(1234)
+                try:
+                    P3 = cls(**make(), paths=11, rng=None)
+                    assert P3.rng is infra.default_rng
+                finally:
+                    infra.default_rng = saved
+                assert keys(P1) == keys(P2) == keys(P3)
+    with pytest.raises(TypeError):          # a seed is not a generator (infrastructure.py:1344)
+        sd.wiener_source(rng=1234)
