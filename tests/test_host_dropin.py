@@ -324,7 +324,7 @@ def test_rng_and_default_rng_reach_every_source():
     from sdepy_b200 import infrastructure as infra
 
     def keys(P):
-        return [(k, s.seed, getattr(getattr(s, 'dn', None), 'seed', None))
+        return [(k, getattr(s, 'seed', None), getattr(getattr(s, 'dn', None), 'seed', None))
                 for k, s in sorted(P.sources.items())]
 
     makers = (
