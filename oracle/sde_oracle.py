@@ -12,8 +12,9 @@ reference (``/root/reference/sdepy`` 1.2.1-dev0, NumPy 2.3.5, SciPy 1.18.1)
 and committed its inputs/outputs under ``tests/golden``;
 ``tests/test_oracle_golden.py`` asserts this module reproduces every one of
 them BIT-EXACTLY (replay mode: same pre-drawn increments; self-driven mode:
-same ``numpy.random`` generator and seed).  The one unpinned piece is the
-Milstein scheme, which the reference does not ship (see ``milstein`` below).
+same ``numpy.random`` generator and seed).  The Milstein scheme, which the
+reference does not ship, is pinned to the reference's integrator machinery
+running it as a plug-in through the ``method=`` hook (see ``milstein`` below).
 
 Third-party arithmetic on the reference path that is not under
 /root/reference: ``numpy.random.Generator.normal / multivariate_normal /
@@ -303,11 +304,14 @@ def system_replay(sde, q, params, x0s, grid, where, dW, addaxis, dN=None, dJ=Non
 def milstein(x, terms, dz, b_dx):
     """Milstein update ``x + a ds + b dw + (1/2) b b' (dw^2 - ds)``.
 
-    PARITY UNPINNED: sdepy ships Euler-Maruyama only (integration.py:615-618).
-    The scheme is plugged into the reference through its documented
-    ``method='<id>'`` -> ``<id>_next`` hook (integration.py:675-685); this is
-    the arithmetic such a plug-in performs, every product and sum separately
-    rounded, Euler part first (same association as integration.py:718).
+    sdepy ships Euler-Maruyama only (integration.py:615-618), so there is no
+    reference Milstein to copy.  PINNED instead to the reference's own integrator
+    machinery running the scheme through its documented ``method='<id>'`` ->
+    ``<id>_next`` hook (integration.py:675-685): tests/golden/
+    make_milstein_plugin.py plugs a ``milstein_next`` (the reference's
+    ``euler_next`` followed by this correction, every product and sum separately
+    rounded) into a class generated by ``sdepy.integrate`` and records the run;
+    tests/test_oracle_golden.py reproduces it bit for bit.
     """
     a = dict((k, c) for c, k in terms)
     ds, dw = dz['dt'], dz['dw']

@@ -146,7 +146,8 @@ def test_milstein_replay_matches_oracle_and_beats_euler():
                             diffusion_dx=lambda t, x, mu, sigma: sigma)
     oe = orc.generic_replay(f, par, 1., grid, [0, n], dW)
     assert np.array_equal(xe, oe)
-    # PARITY UNPINNED (the reference has no Milstein): oracle restatement only
+    # the oracle's Milstein is pinned to the reference machinery + plug-in fixture
+    # (test_milstein_replay_matches_the_reference_machinery_fixture below)
     assert np.abs(xm/om - 1).max() < 1e-12
     exact = np.exp((.05 - .08)*1. + .4*dW.sum(axis=0))
     err_m, err_e = np.abs(xm[-1] - exact).mean(), np.abs(xe[-1] - exact).mean()
@@ -344,3 +345,29 @@ def test_reference_test_SDE_cases():
         return ({'dt': 1, 'dw': 1}, {'dt': 1}, {'dw': 1}, {})
     xs = f_process(x0=(1,)*4, paths=11, steps=30)(t)
     assert np.allclose(np.asarray(xs[1])[-1], 2.) and np.array_equal(np.asarray(xs[3])[-1], np.ones(11))
+
+
+def test_milstein_replay_matches_the_reference_machinery_fixture():
+    """tests/golden/replay_milstein_plugin.npz = the unmodified reference
+    integrator running a Milstein scheme plugged in through its ``method=``
+    hook (make_milstein_plugin.py; the oracle reproduces it bit for bit,
+    tests/test_oracle_golden.py).  Kernel within the north-star 1e-12."""
+    from tests.cases import golden
+    m = sd()
+    g = golden('replay_milstein_plugin')
+
+    def gbm(t, x, mu=.05, sigma=.4):
+        return {'dt': mu*x, 'dw': sigma*x}
+
+    def cev(t, x, mu=0., sigma=1.):
+        return {'dt': mu*x, 'dw': sigma*x**1.5}
+
+    cases = (('gbm', gbm, dict(mu=.05, sigma=.4), 1.),
+             ('cev', cev, dict(mu=lambda t: .02 + .03*t, sigma=lambda t: .3 - .1*t), .8))
+    for name, f, par, x0 in cases:
+        grid, tt, dW, want = (g[name + '_' + k] for k in ('grid', 'tt', 'dW', 'x'))
+        P = m.integrate(f)(paths=dW.shape[-1], steps=grid, x0=x0, method='milstein',
+                           dw=m.replay_source(dW), **par)
+        x = np.asarray(P(tt))
+        assert x.shape == want.shape
+        assert np.abs(x/want - 1).max() < 1e-12, name

@@ -208,3 +208,30 @@ def test_host_process_container_matches_reference():
         assert np.array_equal(q(g['s']), g['piecewise_' + mode]), mode
     with pytest.raises(ValueError):
         m.piecewise(g['t'], v=g['x'][..., 0], mode='centre')
+
+
+def _milstein_cases():
+    g = golden('replay_milstein_plugin')
+
+    def gbm(t, x, mu=.05, sigma=.4):
+        return {'dt': mu*x, 'dw': sigma*x}
+
+    def cev(t, x, mu=0., sigma=1.):
+        return {'dt': mu*x, 'dw': sigma*x**1.5}
+    yield ('gbm', gbm, dict(mu=.05, sigma=.4), 1., lambda t, x, mu, sigma: sigma, g)
+    yield ('cev', cev, dict(mu=lambda t: .02 + .03*t, sigma=lambda t: .3 - .1*t), .8,
+           lambda t, x, mu, sigma: 1.5*sigma*x**.5, g)
+
+
+def test_milstein_pinned_to_the_reference_machinery_with_a_plugged_in_scheme():
+    """The reference ships no Milstein; its documented ``method='<id>'`` hook
+    (integration.py:675-685) runs one: tests/golden/make_milstein_plugin.py adds a
+    ``milstein_next`` to a class made by the unmodified ``sdepy.integrate`` and
+    records the result.  The oracle's restatement of the whole run (grid, left-point
+    parameters, Euler part, correction term) must reproduce it bit for bit."""
+    for name, f, par, x0, b_dx, g in _milstein_cases():
+        grid, tt, dW, want = (g[name + '_' + k] for k in ('grid', 'tt', 'dW', 'x'))
+        where = [int(np.flatnonzero(grid == t)[0]) for t in tt]
+        got = orc.generic_replay(f, par, x0, grid, where, dW, scheme='milstein',
+                                 diffusion_dx=b_dx)
+        assert np.array_equal(got, want), name
