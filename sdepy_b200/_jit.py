@@ -313,14 +313,14 @@ def _compile(source, name):
 JIT_ENTRIES = [
     '#ifndef SDEB_JIT_NO_GENERAL',
     'extern "C" __global__ void __launch_bounds__(SDEB_THREADS, SDEB_MIN_BLOCKS)',
-    'sdeb_jit_entry(const sdeb::KArgs a) { sdeb::integrate_body<sdeb::UserModel, false>(a); }',
+    'sdeb_jit_entry(const sdeb::KArgs a) { sdeb::integrate_body<sdeb::UserModel, false, 1>(a); }',
     '#endif',
     '#ifndef SDEB_JIT_NO_LEAN',
     'extern "C" __global__ void __launch_bounds__(SDEB_THREADS, 1)',
     'sdeb_jit_entry_lean(const sdeb::KArgs a) {',
     '    if (sdeb::UserModel::NPC + (sdeb::UserModel::NDW > 1 ? sdeb::UserModel::NDW *',
     '        (sdeb::UserModel::NDW + 1) / 2 : 0) <= sdeb::MAX_CBANK_PARAMS)',
-    '        sdeb::integrate_body<sdeb::UserModel, true>(a);',
+    '        sdeb::integrate_body<sdeb::UserModel, true,\n            sdeb::UserModel::JUMPS ? 1 : SDEB_LEAN_PPT>(a);',
     '}',
     '#endif',
     '']
@@ -380,7 +380,11 @@ class _traced:
         iterates a set, integration.py:1725-1729)."""
         tr = tracer()
         xs = [tr.var(i) for i in range(self._nvars)]
-        A = self.sde(t, *xs, **self._sde_args_at(t))
+        # t enters as a NumPy scalar, never as a Python float: a Python number
+        # is a structural literal baked into the generated source, whereas
+        # anything derived from the time (t*x, a*(t - x), {'dt': t}) must
+        # become a slot of the per-step parameter record
+        A = self.sde(np.float64(t), *xs, **self._sde_args_at(t))
         self._check_sde_values(A)
         eqs = A if self._system else (A,)
         ids = sorted(set().union(*[set(a.keys()) for a in eqs]))

@@ -94,10 +94,11 @@ static const int64_t kMaxStatsSmem = 96 * 1024;   // accumulators kept in smem u
 static int64_t smem_bytes(const ModelInfo& mi, const sdeb_problem* p, bool stats_in_kernel) {
     int64_t nch = mi.ndw > 1 ? (int64_t)mi.ndw * (mi.ndw + 1) / 2 : 0;
     int64_t npt = mi.npc + nch;
-    // dynamic part only: tables and the staged step block are static __shared__;
+    // dynamic part only (generator tables first); the staged step block is static __shared__;
     // parameter records are staged only when time-dependent and shared by the paths
     const bool staged = p->n_psteps > 1 && !p->params_per_path;
-    int64_t d = (staged ? (int64_t)STEP_CHUNK * npt : 0) + 8 * NSTAT * mi.nx;
+    int64_t d = (int64_t)TAB_DOUBLES * SDEB_TAB_COPIES +
+                (staged ? (int64_t)STEP_CHUNK * npt : 0) + 8 * NSTAT * mi.nx;
     if (stats_in_kernel) d += p->n_rows * p->n_groups * mi.nx * NSTAT;
     int64_t bytes = d * 8;
     if (p->noise == SDEB_NOISE_REPLAY)       // cp.async ring of the replay table
@@ -145,12 +146,12 @@ static int plan_impl(const sdeb_problem* p, sdeb_plan_t* plan, ModelInfo& mi, bo
     plan->stats_in_kernel = (acc <= kMaxStatsSmem) ? 1 : 0;
     bool sik = p->stats != NULL && plan->stats_in_kernel;
     plan->smem_bytes = smem_bytes(mi, p, sik);
-    // 227 KB per CTA on sm_100a, ~10 KB of it static (tables, step block)
-    if (plan->smem_bytes > (227 - 10) * 1024)
+    // 227 KB per CTA on sm_100a, ~2 KB of it static (step block, store rows)
+    if (plan->smem_bytes > (227 - 2) * 1024)
         return fail(SDEB_EINVAL,
                     "this model does not fit the per-block shared memory (" +
                     std::to_string(plan->smem_bytes / 1024) + " KB of staged parameter records "
-                    "and replay ring needed, 217 KB available): too many correlated components "
+                    "and replay ring needed, 225 KB available): too many correlated components "
                     "for time-dependent parameters and/or replayed increments");
     int64_t tiles = ((p->n_paths + kThreads - 1) / kThreads) * p->n_groups;
     int sm = 148, occ = 2;
@@ -165,7 +166,7 @@ static int plan_impl(const sdeb_problem* p, sdeb_plan_t* plan, ModelInfo& mi, bo
     const void* fn = use_lean(p, mi) ? mi.fn_lean : mi.fn;
     if (e == cudaSuccess && fn) {
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
-        if (plan->smem_bytes > 32 * 1024)   // + ~10 KB of static shared memory
+        if (plan->smem_bytes > 32 * 1024)   // + ~2 KB of static shared memory
             cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)plan->smem_bytes);
         int o = 0;
@@ -761,8 +762,9 @@ extern "C" int sdeb_histogram(const double* x, int64_t n, const double* edges, i
 __global__ void __launch_bounds__(256)
 draw_wiener_kernel(const NrmK nk, double* out, int n_groups, int ndw, int64_t n_paths, int64_t pitch,
                    int64_t path_offset, u64 seed, u32 step, double sq, const double* chol) {
-    __shared__ __align__(16) double tab[TAB_DOUBLES];
-    fill_tables(tab);
+    __shared__ __align__(16) double tab_mem[TAB_DOUBLES];
+    fill_tables(tab_mem);
+    const Tab tab(tab_mem);
     __syncthreads();
     const int64_t path = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int g = blockIdx.y;
@@ -777,8 +779,8 @@ draw_wiener_kernel(const NrmK nk, double* out, int n_groups, int ndw, int64_t n_
     double z[36];
     for (int b = 0; b < (ndw + 3) / 4; ++b) {      // one block = two pairs
         U4 w = rng.block((u32)b);
-        normal_pair(w.x, w.y, tab, nk, 1.0, z[4*b], z[4*b + 1], TailDraw{rng, (u32)(2*b)});
-        normal_pair(w.z, w.w, tab, nk, 1.0, z[4*b + 2], z[4*b + 3], TailDraw{rng, (u32)(2*b + 1)});
+        normal_pair(w.x, w.y, tab, nk, 1.0, z[4*b], z[4*b + 1]);
+        normal_pair(w.z, w.w, tab, nk, 1.0, z[4*b + 2], z[4*b + 3]);
     }
     for (int r = ndw - 1; r >= 0; --r) {
         double acc = z[r];
@@ -814,9 +816,10 @@ __global__ void __launch_bounds__(256)
 bridge_wiener_kernel(const NrmK nk, double* out, const double* w1, const double* w2,
                      const double* mats, int ndw, int64_t n_paths, int64_t pitch,
                      int64_t path_offset, u64 seed, u32 step) {
-    __shared__ __align__(16) double tab[TAB_DOUBLES];
+    __shared__ __align__(16) double tab_mem[TAB_DOUBLES];
     __shared__ double s_m[3 * 32 * 32];
-    fill_tables(tab);
+    fill_tables(tab_mem);
+    const Tab tab(tab_mem);
     for (int i = threadIdx.x; i < 3 * ndw * ndw; i += blockDim.x) s_m[i] = mats[i];
     __syncthreads();
     const int64_t path = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -832,8 +835,8 @@ bridge_wiener_kernel(const NrmK nk, double* out, const double* w1, const double*
     double z[36];
     for (int b = 0; b < (ndw + 3) / 4; ++b) {      // one block = two pairs
         U4 w = rng.block((u32)b);
-        normal_pair(w.x, w.y, tab, nk, 1.0, z[4*b], z[4*b + 1], TailDraw{rng, (u32)(2*b)});
-        normal_pair(w.z, w.w, tab, nk, 1.0, z[4*b + 2], z[4*b + 3], TailDraw{rng, (u32)(2*b + 1)});
+        normal_pair(w.x, w.y, tab, nk, 1.0, z[4*b], z[4*b + 1]);
+        normal_pair(w.z, w.w, tab, nk, 1.0, z[4*b + 2], z[4*b + 3]);
     }
     const double* M1 = s_m; const double* M2 = s_m + ndw * ndw; const double* Ly = s_m + 2 * ndw * ndw;
     for (int r = 0; r < ndw; ++r) {
@@ -867,8 +870,9 @@ __global__ void __launch_bounds__(256)
 draw_cpoisson_kernel(const NrmK nk, double* dj, i64* dn, int64_t n_paths, int64_t pitch, int64_t path_offset,
                      u64 seed, u32 step, double lamdt, double explam, int sign, int law,
                      double a, double b, double pa) {
-    __shared__ __align__(16) double tab[TAB_DOUBLES];
-    fill_tables(tab);
+    __shared__ __align__(16) double tab_mem[TAB_DOUBLES];
+    fill_tables(tab_mem);
+    const Tab tab(tab_mem);
     __syncthreads();
     const int64_t path = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int g = blockIdx.y;
@@ -881,10 +885,10 @@ draw_cpoisson_kernel(const NrmK nk, double* dj, i64* dn, int64_t n_paths, int64_
     rng.c_x = (u32)gpath; rng.c_y = ((u32)(gpath >> 32) & 0xFFu) | ((u32)g << 8);
     rng.step = step;
     U4 w = rng.block((u32)STREAM_POISSON);
-    int k = poisson_inv(u01(w.x, w.y), lamdt, explam);
+    int k = poisson_draw(u01(w.x, w.y), lamdt, rng, 0u);
     double sum = 0.0;
     for (int j = 0; j < k; ++j) {
-        U4 wj = rng.block((u32)(STREAM_JUMP + j));
+        U4 wj = rng.block((u32)(STREAM_JUMP + (j & 0x3FFF)));
         double yj = jump_size(wj, tab, nk, law, a, b, pa);
         sum = (j == 0) ? yj : sum + yj;
     }
@@ -913,8 +917,9 @@ extern "C" int sdeb_draw_cpoisson(double* dj, int64_t* dn, int64_t n_lanes, int6
 // self tests / measurement
 // ---------------------------------------------------------------------------
 __global__ void test_normals_kernel(const NrmK nk, u64 seed, int64_t n, double* zf, double* zl) {
-    __shared__ __align__(16) double tab[TAB_DOUBLES];
-    fill_tables(tab);
+    __shared__ __align__(16) double tab_mem[TAB_DOUBLES];
+    fill_tables(tab_mem);
+    const Tab tab(tab_mem);
     __syncthreads();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -924,17 +929,19 @@ __global__ void test_normals_kernel(const NrmK nk, u64 seed, int64_t n, double* 
     rng.rk = rk;
     rng.c_x = (u32)i; rng.c_y = (u32)(i >> 32); rng.step = 0;
     U4 w = rng.block(0);
-    if (i < 128) {   // force the extreme corners of the bit space through both maps
-        if (i & 1) { w.x &= 0x000FFFFFu; w.z = 0; }            // e = 45: deepest tail
-        if (i & 2) { w.x |= 0x000FFFFFu; w.y |= 0xFF000000u; } // m -> 2
-        if (i & 4) { w.x &= 0xFFF00000u; w.y &= 0x00FFFFFFu; } // m = 1
-        if (i & 8) w.x |= 0x80000000u;  // e = 1
-        if (i & 16) w.y |= 0x00FFFFFFu; // last sector, largest offset
-        if (i & 32) w.y &= 0xFF000000u; // first sector, most negative offset
-        if (i & 64) { w.x &= 0x000FFFFFu; w.z = 0x80000000u; } // e = 13
+    const bool full = i >= n / 2;      // second half: the 96-bit full-resolution map
+    if ((i % (n / 2 > 0 ? n / 2 : 1)) < 128) {   // force the extreme corners of the bit space through both maps
+        if (i & 1) { w.x = 0; w.z = 0; }                          // smallest u: deepest tail
+        if (i & 2) { w.x = 0xFFFFFFFFu; w.z = 0xFFFFFFFFu; }      // largest u
+        if (i & 4) { w.x &= 0xFFF00000u; w.z &= 0x00000FFFu; }    // top mantissa bits clear
+        if (i & 8) w.x |= 0x00080000u;                            // u >= 1/2: e = 1
+        if (i & 16) w.y |= 0x00FFFFFFu;                           // largest offset in the sector
+        if (i & 32) w.y &= 0xFF000000u;                           // most negative offset
+        if (i & 64) w.y |= 0xFF000000u;                           // last sector
     }
-    normal_pair(w.x, w.y, tab, nk, 1.0, zf[2*i], zf[2*i + 1], TailWord{w.z});
-    normal_pair_libdevice(w.x, w.y, zl[2*i], zl[2*i + 1], TailWord{w.z});
+    if (full) normal_pair_full(w.x, w.z, w.y, tab, nk, 1.0, zf[2*i], zf[2*i + 1]);
+    else normal_pair(w.x, w.y, tab, nk, 1.0, zf[2*i], zf[2*i + 1]);
+    normal_pair_libdevice(w.x, w.z, w.y, full, zl[2*i], zl[2*i + 1]);
 }
 
 extern "C" int sdeb_test_normals(uint64_t seed, int64_t n, double* z_fast, double* z_libdevice,

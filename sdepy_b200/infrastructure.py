@@ -833,7 +833,11 @@ class source:
         """Fresh 64-bit Philox key for one integration (or one draw call):
         successive runs of the same instance are independent, the same
         (seed, call index) always reproduces the same stream."""
-        key = _splitmix64(self.seed + self._epoch)
+        # seed and call index are hashed as SEPARATE words: with seed + epoch,
+        # call n of seed s would reuse the key of call 0 of seed s + n, i.e.
+        # `for seed in range(k)` loops with repeated calls would repeat paths
+        key = _splitmix64(_splitmix64(self.seed & 0xFFFFFFFFFFFFFFFF) ^
+                          ((self._epoch*0xD1342543DE82EF95) & 0xFFFFFFFFFFFFFFFF))
         self._epoch += 1
         return key
 

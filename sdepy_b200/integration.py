@@ -220,32 +220,29 @@ class path_stats:
         self.info = info
 
     def allreduce(self, group=None):
-        """Combine the shards of all ranks: ONE collective over the packed
-        vector (power sums and payoff sums add, min/max and the path count ride
-        along).  NCCL when the process group is NCCL, gloo on CPU."""
+        """Combine the shards of all ranks with ONE all-reduce (SUM): every rank
+        places its packed block (centre, power sums, min, max, payoff sums, path
+        count) in its own slot of a [world, ...] vector, so that after the
+        collective each rank holds all the blocks and folds them in rank order
+        -- re-centring the power sums on rank 0's centre first (the centres
+        differ when x0 is path-dependent).  NCCL when the process group is NCCL,
+        gloo on CPU."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()):
             return self
         backend = dist.get_backend(group)
         dev = torch.device('cuda', torch.cuda.current_device()) if backend == 'nccl' else 'cpu'
-        s = self.sums
-        add = np.concatenate((s[..., :4].ravel(), s[..., 6:].ravel(), [float(self.paths)]))
-        # min/max share the SUM collective through a one-hot layout per rank
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        mm = np.zeros((world, 2*s[..., 4].size))
-        mm[rank] = np.concatenate((s[..., 4].ravel(), s[..., 5].ravel()))
-        buf = torch.from_numpy(np.concatenate((add, mm.ravel()))).to(dev)
+        s = self.sums
+        c = np.broadcast_to(self.centre, s.shape[1:-1]) if s.ndim > 1 else self.centre
+        c = np.broadcast_to(c, s.shape[:-1])
+        block = np.concatenate((s.ravel(), c.ravel(), [float(self.paths)]))
+        buf = np.zeros((world, block.size))
+        buf[rank] = block
+        buf = torch.from_numpy(buf).to(dev)
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         buf = buf.cpu().numpy()
-        n4, n2 = s[..., :4].size, s[..., 6:].size
-        out = np.empty_like(s)
-        out[..., :4] = buf[:n4].reshape(s[..., :4].shape)
-        out[..., 6:] = buf[n4:n4 + n2].reshape(s[..., 6:].shape)
-        paths = int(round(buf[n4 + n2]))
-        mm = buf[n4 + n2 + 1:].reshape(world, 2, -1)
-        out[..., 4] = mm[:, 0].min(axis=0).reshape(s[..., 4].shape)
-        out[..., 5] = mm[:, 1].max(axis=0).reshape(s[..., 5].shape)
-        return path_stats(self.t, out, self.centre, paths, self.info)
+        return _fold_rank_blocks(self, buf)
 
     def _m(self, k):
         return self.sums[..., k - 1]/self.paths
@@ -287,6 +284,42 @@ class path_stats:
         n = self.paths
         m, m2 = self.sums[..., 6]/n, self.sums[..., 7]/n
         return self._proc(np.sqrt(np.maximum(m2 - m*m, 0.)/(n - 1)))
+
+
+def _fold_rank_blocks(proto, buf):
+    """Fold the per-rank blocks [world, sums | centres | paths] of
+    ``path_stats.allreduce`` in rank order; power sums about centre c_r are
+    moved to rank 0's centre c_0 binomially (d = c_r - c_0)."""
+    s0 = proto.sums
+    ns, nc = s0.size, s0[..., 0].size
+    out, c0, paths = None, None, 0
+    for r in range(buf.shape[0]):
+        s = buf[r, :ns].reshape(s0.shape).copy()
+        c = buf[r, ns:ns + nc].reshape(s0.shape[:-1])
+        n = int(round(buf[r, ns + nc]))
+        if n == 0:
+            continue
+        if out is None:
+            out, c0, paths = s, c, n
+            continue
+        d = c - c0
+        S1, S2, S3, S4 = (s[..., k] for k in range(4))
+        if np.any(d != 0.):
+            T1 = S1 + n*d
+            T2 = S2 + 2*d*S1 + n*d**2
+            T3 = S3 + 3*d*S2 + 3*d**2*S1 + n*d**3
+            T4 = S4 + 4*d*S3 + 6*d**2*S2 + 4*d**3*S1 + n*d**4
+            S1, S2, S3, S4 = T1, T2, T3, T4
+        for k, S in enumerate((S1, S2, S3, S4)):
+            out[..., k] += S
+        out[..., 4] = np.minimum(out[..., 4], s[..., 4])
+        out[..., 5] = np.maximum(out[..., 5], s[..., 5])
+        out[..., 6:] += s[..., 6:]
+        paths += n
+    if out is None:
+        return proto
+    centre = c0[0] if proto.centre.ndim < c0.ndim else c0
+    return path_stats(proto.t, out, centre, paths, proto.info)
 
 
 # --------------------------------------------------------------------------
@@ -423,9 +456,13 @@ class SDE(_jit._traced):
                              rho=rho, **extra)
 
     def source_dn(self, dn=None, ptype=int, lam=1.):
+        """Poisson source (reference 1346-1381); ``SDE(seed=...)`` reaches it
+        like the other Philox-backed sources."""
+        import inspect
+        extra = self._source_kw() if (dn is None or (
+            inspect.isclass(dn) and issubclass(dn, poisson_source))) else dict(rng=self._rng_asis)
         return _source_setup(dn, poisson_source, paths=self.paths,
-                             vshape=self.wshape, dtype=ptype,
-                             rng=self._rng_asis, lam=lam)
+                             vshape=self.wshape, dtype=ptype, lam=lam, **extra)
 
     def source_dj(self, dj=None, dn=None, ptype=int, lam=1., y=None):
         """Compound Poisson source (reference 1383-1423)."""
@@ -702,7 +739,7 @@ class SDE(_jit._traced):
                 return z
             return id(z)
         srcs = []
-        for k in ('dw', 'dj'):
+        for k in ('dw', 'dj', 'dn'):
             src = self.sources.get(k)
             srcs.append((id(src), ident(getattr(src, 'corr', None)), ident(getattr(src, 'lam', None)),
                          id(getattr(src, 'y', None))))

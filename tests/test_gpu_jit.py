@@ -371,3 +371,27 @@ def test_milstein_replay_matches_the_reference_machinery_fixture():
         x = np.asarray(P(tt))
         assert x.shape == want.shape
         assert np.abs(x/want - 1).max() < 1e-12, name
+
+
+def test_explicit_time_in_traced_sde_replay_bit_exact():
+    """A traced function that uses `t` arithmetically with the state and as a
+    coefficient of its own: every step must see its own time (the value used
+    to be frozen at the first trace)."""
+    m = sd()
+
+    def f(t, x, a=2.):
+        return {'dt': a*(t - x), 'dw': 1 + t}
+
+    n, paths = 40, 512
+    grid = np.cumsum(np.concatenate(([0.], np.random.default_rng(5).uniform(.01, .09, n))))
+    rng = np.random.default_rng(3)
+    dW = rng.standard_normal((n, paths))*np.sqrt(np.diff(grid))[:, None]
+    where = [0, n//2, n]
+    P = m.integrate(f)(paths=paths, steps=grid, x0=.5, a=2., dw=m.replay_source(dW))
+    x = np.asarray(P(grid[where]))
+    o = orc.generic_replay(f, dict(a=2.), .5, grid, where, dW)
+    assert np.array_equal(x, o)
+    # the frozen-t result would be a plain OU pulled to 0 with unit diffusion
+    frozen = orc.generic_replay(lambda t, x, a: {'dt': a*(0. - x), 'dw': 1.}, dict(a=2.),
+                                .5, grid, where, dW)
+    assert np.abs(x[-1] - frozen[-1]).max() > .1

@@ -17,36 +17,80 @@ def sd():
     return sdepy_b200
 
 
-def test_normal_pair_matches_libdevice():
+def _test_normals(n, seed=1234):
     from sdepy_b200 import _lib, _cuda
-    n = 1 << 20
     zf = torch.empty(2*n, dtype=torch.float64, device='cuda')
     zl = torch.empty(2*n, dtype=torch.float64, device='cuda')
-    _lib.check(_lib.lib.sdeb_test_normals(1234, n, _cuda.ptr(zf), _cuda.ptr(zl),
+    _lib.check(_lib.lib.sdeb_test_normals(seed, n, _cuda.ptr(zf), _cuda.ptr(zl),
                                           _cuda.stream_ptr(zf.device)))
-    zf, zl = zf.cpu().numpy(), zl.cpu().numpy()
+    return zf, zl
+
+
+def test_normal_pair_matches_libdevice():
+    """First half of the sample: the default 64-bit map (32-bit radius uniform,
+    32-bit direction); second half: the 96-bit full-resolution map.  The first
+    128 pairs of each half force the corners of the bit space."""
+    import scipy.stats
+    n = 1 << 21
+    zf, zl = (z.cpu().numpy() for z in _test_normals(n))
     assert np.isfinite(zf).all()
     # hand-rolled log / sqrt / sincos vs libdevice on identical bits.  Both
     # maps carry ~2e-16 ABSOLUTE error in s2 = -2 ln u, i.e. ~1e-16/r in
     # z = r (cos, sin) -- only visible in the forced corner u -> 1 (r -> 0)
     r = np.maximum(np.hypot(zl[0::2], zl[1::2]), 1e-300).repeat(2)
     assert (np.abs(zf - zl) < 4e-15 + 3e-16/r).all()
-    assert np.abs(zf - zl)[256:].max() < 1e-13
-    z = zf[256:]
-    # radius tail: P(u < 2^-k) = 2^-k on both sides of the 12-bit exponent field
-    # (beyond it the leading-zero count continues in an extra Philox word)
-    r2 = z[0::2]**2 + z[1::2]**2
-    for k in (8, 12, 14, 16):
-        want = r2.size*2.**-k
-        got = (r2 > 2*k*np.log(2.)).sum()
-        assert abs(got - want) < 5*np.sqrt(want), (k, got, want)
-    assert abs(z.mean()) < 4/np.sqrt(z.size)
-    assert abs(z.var() - 1) < 4*np.sqrt(2/z.size)
-    assert abs((z**4).mean() - 3) < 4*np.sqrt(96/z.size)
+    for half, rmax in ((0, np.sqrt(2*33*np.log(2.))), (1, np.sqrt(2*53*np.log(2.)))):
+        z = zf[half*n:(half + 1)*n]
+        zc, z = z[:256], z[256:]
+        assert np.abs(z - zl[half*n:(half + 1)*n][256:]).max() < 1e-13
+        # the forced smallest u reaches the advertised largest radius
+        assert np.isclose(np.hypot(zc[2], zc[3]), rmax, rtol=1e-12)
+        # radius tail: P(u < 2^-k) = 2^-k (the exponent comes from the uniform's own
+        # exponent field: no leading-zero count, no tail draw)
+        r2 = z[0::2]**2 + z[1::2]**2
+        for k in (8, 12, 14, 16):
+            want = r2.size*2.**-k
+            got = (r2 > 2*k*np.log(2.)).sum()
+            assert abs(got - want) < 5*np.sqrt(want), (k, got, want)
+        assert abs(z.mean()) < 4/np.sqrt(z.size)
+        assert abs(z.var() - 1) < 4*np.sqrt(2/z.size)
+        assert abs((z**4).mean() - 3) < 4*np.sqrt(96/z.size)
+        assert scipy.stats.kstest(z[:200000], 'norm').pvalue > 1e-4
+        # pairs are uncorrelated
+        assert abs(np.mean(z[0::2]*z[1::2])) < 4/np.sqrt(z.size/2)
+
+
+def test_normal_draws_fine_grid_and_deep_tails():
+    """2^30 default-map normals, reduced on the device: (i) chi-square of
+    Phi(z) over 2^16 equiprobable cells (fine-grid uniformity), (ii) two-sided
+    tail counts down to 2^-24, each within 5 sigma of its binomial expectation."""
+    cells = 1 << 16
+    hist = torch.zeros(cells, dtype=torch.float64, device='cuda')
+    ks = (12, 16, 20, 24)
     import scipy.stats
-    assert scipy.stats.kstest(z[:200000], 'norm').pvalue > 1e-4
-    # pairs are uncorrelated
-    assert abs(np.mean(z[0::2]*z[1::2])) < 4/np.sqrt(z.size/2)
+    thr = [float(scipy.stats.norm.isf(2.**-(k + 1))) for k in ks]      # P(|z| > thr) = 2^-k
+    tails = np.zeros(len(ks))
+    total = 0
+    n = 1 << 26                       # pairs per call: 2^27 doubles per array
+    for it in range(8):
+        zf, _ = _test_normals(n, seed=77 + it)
+        z = zf[:n][256:]              # default map, corners dropped
+        p = torch.special.ndtr(z)
+        idx = torch.clamp((p*cells).to(torch.int64), 0, cells - 1)
+        hist += torch.bincount(idx, minlength=cells).to(torch.float64)
+        az = z.abs()
+        tails += np.array([float((az > t).sum()) for t in thr])
+        total += z.numel()
+        del zf, z, p, idx, az
+    h = hist.cpu().numpy()
+    assert h.sum() == total
+    exp = total/cells
+    chi2 = ((h - exp)**2/exp).sum()
+    # chi-square with cells-1 degrees of freedom: mean cells-1, sd sqrt(2(cells-1))
+    assert abs(chi2 - (cells - 1)) < 5*np.sqrt(2*(cells - 1)), chi2
+    for k, got in zip(ks, tails):
+        want = total*2.**-k
+        assert abs(got - want) < 5*np.sqrt(want) + 1, (k, got, want)
 
 
 def test_philox_mode_equals_replay_of_its_own_increments():

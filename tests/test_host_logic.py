@@ -151,6 +151,46 @@ def test_same_seed_same_keys():
     assert c.seed == 42
 
 
+def test_keys_distinct_over_seed_epoch_grid():
+    """Adjacent seeds must not share streams on successive calls (the key of
+    call n of seed s used to equal the key of call 0 of seed s + n)."""
+    keys = set()
+    for seed in range(64):
+        src = sd.wiener_source(paths=2, seed=seed)
+        for _ in range(64):
+            keys.add(src.next_key())
+    assert len(keys) == 64*64
+    a, b = sd.wiener_source(paths=2, seed=0), sd.wiener_source(paths=2, seed=1)
+    a.next_key()
+    assert a.next_key() != b.next_key()
+    P0, P1 = (sd.lognorm_process(paths=2, seed=s) for s in (0, 1))
+    P0._philox_key()
+    assert P0._philox_key() != P1._philox_key()
+
+
+def test_explicit_time_in_traced_sde_is_a_record_slot():
+    """`t` used arithmetically inside a traced function must vary from step to
+    step (it used to be frozen at its value at the first trace)."""
+    from sdepy_b200 import _jit
+
+    def f(t, x, a=2.):
+        return {'dt': a*(t - x), 'dw': 1 + t}
+
+    P = sd.integrate(f)(paths=4, a=2.)
+    tr0, r0 = P._trace(0.)
+    tr1, r1 = P._trace(.5)
+    assert tr0.signature(r0) == tr1.signature(r1)
+    assert not any(getattr(l, 'literal', False) and float(l.value) == 0. for l in tr0.leaves)
+    x = np.array([.1, .2, .3])
+    for t, (tr, roots) in ((0., (tr0, r0)), (.5, (tr1, r1))):
+        got = {k: _jit.evaluate(n, [x]) for k, n in roots[0]}
+        want = f(t, x)
+        assert np.array_equal(got['dt'], want['dt'])
+        assert np.array_equal(np.broadcast_to(got['dw'], x.shape), np.broadcast_to(want['dw'], x.shape))
+    src = P._codegen(tr0, r0, [None])
+    assert 'xsub(0.0' not in src and 'xmul(0.0' not in src
+
+
 def test_process_container():
     t = np.linspace(0, 1, 5)
     x = np.arange(5*2*3, dtype=float).reshape(5, 2, 3)

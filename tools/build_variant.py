@@ -22,7 +22,10 @@ import _build  # noqa: E402
 
 def main():
     name, flags = sys.argv[1], sys.argv[2:]
-    _build.build()
+    if '--no-rebuild' in flags:      # link against the objects as they are (stale or not)
+        flags.remove('--no-rebuild')
+    else:
+        _build.build()
     out = os.path.join(ROOT, 'gpurun_variants')
     os.makedirs(out, exist_ok=True)
     obj = os.path.join(out, 'unit0_%s.o' % name)

@@ -29,12 +29,12 @@ struct PArgs {
     unsigned long long* neg;
 };
 
-template <int PPT, int MINB>
+template <int PPT, int MINB, int COPIES>
 __global__ void __launch_bounds__(256, MINB) heston_probe(const PArgs a) {
-    __shared__ __align__(16) double tab_mem[TAB_DOUBLES];
-    fill_tables(tab_mem);
+    extern __shared__ __align__(16) double tab_mem[];
+    fill_tables_t<COPIES>(tab_mem);
     __syncthreads();
-    const Tab tab(tab_mem, a.nk.v[14]);
+    const TabT<COPIES> tab(tab_mem, a.nk.v[14]);
     typedef HestonSDE<1, false> M;
     double sx = 0.0, sy = 0.0;
     unsigned long long negs = 0;
@@ -63,9 +63,9 @@ __global__ void __launch_bounds__(256, MINB) heston_probe(const PArgs a) {
             for (int q = 0; q < PPT; ++q) {
                 double z[2];
                 rng[q].step = (u32)(n >> 1);
-                normal_pair(cur[q].x, cur[q].y, tab, a.nk, a.sq, z[0], z[1], TailDraw{rng[q], 0u});
+                normal_pair(cur[q].x, cur[q].y, tab, a.nk, a.sq, z[0], z[1]);
                 z[1] = fma(a.pc[8], z[1], a.pc[7]*z[0]);
-                M::step(x[q], a.pc, a.ds, z, z, cnt[q], tab.k375);
+                M::step<false>(x[q], a.pc, a.ds, z, z, cnt[q], tab.k375);
             }
             // next period's block, drawn while step n+1 runs (as the engine does)
 #pragma unroll
@@ -77,9 +77,9 @@ __global__ void __launch_bounds__(256, MINB) heston_probe(const PArgs a) {
             for (int q = 0; q < PPT; ++q) {
                 double z[2];
                 rng[q].step = (u32)(n >> 1);
-                normal_pair(cur[q].z, cur[q].w, tab, a.nk, a.sq, z[0], z[1], TailDraw{rng[q], 1u});
+                normal_pair(cur[q].z, cur[q].w, tab, a.nk, a.sq, z[0], z[1]);
                 z[1] = fma(a.pc[8], z[1], a.pc[7]*z[0]);
-                M::step(x[q], a.pc, a.ds, z, z, cnt[q], tab.k375);
+                M::step<false>(x[q], a.pc, a.ds, z, z, cnt[q], tab.k375);
             }
         }
 #pragma unroll
@@ -99,26 +99,29 @@ __global__ void __launch_bounds__(256, MINB) heston_probe(const PArgs a) {
     }
 }
 
-template <int PPT, int MINB>
+template <int PPT, int MINB, int COPIES>
 void run(const PArgs& base, int sm) {
+    const size_t smem = (size_t)TAB_DOUBLES*COPIES*8;
+    auto kern = heston_probe<PPT, MINB, COPIES>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     PArgs a = base;
     cudaMemset(a.sum, 0, 16); cudaMemset(a.neg, 0, 8);
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, heston_probe<PPT, MINB>, 256, 0);
-    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, heston_probe<PPT, MINB>);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem);
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
     const int grid = sm*(occ > 0 ? occ : 1);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     PArgs w = a; w.n_paths = a.n_paths/8;
-    heston_probe<PPT, MINB><<<grid, 256>>>(w);                 // warm-up
+    kern<<<grid, 256, smem>>>(w);                 // warm-up
     cudaMemset(a.sum, 0, 16); cudaMemset(a.neg, 0, 8);
     cudaEventRecord(e0);
-    heston_probe<PPT, MINB><<<grid, 256>>>(a);
+    kern<<<grid, 256, smem>>>(a);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     double h[2]; unsigned long long neg;
     cudaMemcpy(h, a.sum, 16, cudaMemcpyDeviceToHost); cudaMemcpy(&neg, a.neg, 8, cudaMemcpyDeviceToHost);
-    printf("paths/thread=%d min_blocks=%d: %3d regs, %d CTAs/SM, %8.3f ms, %.4g path-steps/s  "
-           "mean log x_T=%.12f mean y_T=%.12f neg=%llu  (%s)\n", PPT, MINB, fa.numRegs, occ, ms,
+    printf("paths/thread=%d min_blocks=%d table copies=%d: %3d regs, %d CTAs/SM, %8.3f ms, %.4g path-steps/s  "
+           "mean log x_T=%.12f mean y_T=%.12f neg=%llu  (%s)\n", PPT, MINB, COPIES, fa.numRegs, occ, ms,
            (double)a.n_paths*a.n_steps/(ms*1e-3), h[0]/a.n_paths, h[1]/a.n_paths, neg,
            cudaGetErrorString(cudaGetLastError()));
 }
@@ -135,9 +138,14 @@ int main() {
     a.n_steps = 252; a.ds = 1.0/252; a.sq = 0.06299407883487121;   // sqrt(1/252)
     a.n_paths = 20000000;
     cudaMalloc(&a.sum, 16); cudaMalloc(&a.neg, 8);
-    run<1, 2>(a, sm);          // the product's layout: 1 path per thread, 2 CTAs per SM
-    run<2, 1>(a, sm);          // 2 paths per thread, whatever occupancy the registers allow
-    run<2, 2>(a, sm);          // 2 paths per thread squeezed under 128 registers
-    run<1, 3>(a, sm);
+    run<1, 2, 1>(a, sm);       // round 1's layout: 1 path per thread, 2 CTAs per SM, one table copy
+    run<1, 2, 8>(a, sm);       // ... with 8 interleaved table copies (conflict-free look-ups)
+    run<1, 3, 8>(a, sm);
+    run<2, 1, 1>(a, sm);       // 2 paths per thread, whatever occupancy the registers allow
+    run<2, 1, 8>(a, sm);
+    run<2, 2, 1>(a, sm);       // 2 paths per thread squeezed under 128 registers
+    run<2, 2, 8>(a, sm);
+    run<3, 1, 8>(a, sm);
+    run<4, 1, 8>(a, sm);
     return 0;
 }
