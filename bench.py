@@ -23,8 +23,19 @@ the single all-reduce of the packed statistics vector).
           Heston path-step at libdevice transcendental costs) x path-steps/s,
           peak = DFMA rate measured live by sdeb_fp64_peak(); both in TFLOP/s
           (2 flop per FP64 lane-instruction).  roofline.executed reports the
-          pipe utilisation of what the kernel really issues (53 FP64
-          instructions per path-step; = ncu sm__pipe_fp64_cycles_active).
+          pipe utilisation of what the kernel really issues (FP64-pipe
+          instructions per path-step from the committed ncu counters,
+          profiles/r02_lean_heston_counters.json; = ncu
+          sm__pipe_fp64_cycles_active); roofline.issue the issue-slot
+          utilisation (all warp instructions per warp-step over the cycles
+          per warp-step measured in THIS run).
+  strong : the same workload with 1e8 GLOBAL paths split over the N ranks
+          (value, e2e, efficiency against this run's single-GPU time for 1e8).
+  modes  : the HBM-bound full-path configurations (C2a OU, C2b HW-3f, replayed
+          OU) measured in this run: stored GB/s against MEASURED_PEAKS.json.
+  check  : Monte Carlo price vs closed form, and BASELINE config 5 (custom
+          @integrate SDE, Milstein, montecarlo histogram + moments) sharded over
+          the ranks and all-reduced vs a single-process recompute.
   cpu_baseline : the NumPy oracle port of the reference's Heston path, one
           core, on a bounded sample, same box, same run.
 
@@ -54,18 +65,17 @@ STRIKE, RATE = 100., .03
 # counting each sqrt/log/sin/cos as one = ~100 FP64-pipe instructions with
 # libdevice transcendental costs.  This is the per-unit figure of the roofline.
 ALGO_FP64_INSTR_PER_PATH_STEP = 100
-# FP64-pipe warp-instructions this kernel actually EXECUTES per path-step
-# (hand-rolled log / sqrt / sincos): DFMA+DMUL+DADD+DSETP on the Philox /
-# no-store path of integrate_lean_kernel<HestonSDE<1,false>>, SASS count,
-# confirmed by ncu sm__inst_executed_pipe_fp64.sum / path-steps = 53.5
-N64_PER_PATH_STEP = 53
-# dram__bytes_read.sum + dram__bytes_write.sum of integrate_lean_kernel<Heston> from the
-# ncu --set full capture in profiles/r01_ncu_integrate_lean_heston.csv (1e7 paths x 252
-# steps per launch): 80.18 MB read + 22.15 MB written = the per-path int64
-# `negative_y_count` diagnostic (getinfo=True, the reference's default: 8 B read per path,
-# 8 B written back, part of it still in L2 when the kernel ends); the tables in and the
-# per-CTA partial sums out are KBs.  10.2 B per path, once per launch -- not per step.
-NCU_DRAM_BYTES_PER_PATH = (80.182528e6 + 22.148864e6)/1e7
+# What the kernel actually EXECUTES per path-step, and its DRAM traffic, are NOT
+# constants of this file: they are read from the committed ncu counters of the
+# dominant kernel (tools/ncu_counters.py over the `--set full` capture; the JSON
+# names the commit and the command it was taken at).
+COUNTERS_FILE = os.path.join(ROOT, 'profiles', 'r02_lean_heston_counters.json')
+N_SMSP = 148*4              # B200: SM sub-partitions (issue ports)
+
+
+def load_counters():
+    with open(COUNTERS_FILE) as f:
+        return json.load(f)
 
 
 def parse():
@@ -207,11 +217,141 @@ class clock_sampler:
 # GPU arm
 # ---------------------------------------------------------------------------
 
+def measured_hbm_peak():
+    """(GB/s, source): MEASURED_PEAKS.json (driver-written), else the profiling
+    recipe's fallback."""
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs'
+    except Exception:
+        return 6553.6, 'fallback of B200_PROFILING.md (no MEASURED_PEAKS.json)'
+
+
+def full_path_modes(sd, torch, dev):
+    """The HBM-bound output mode: full paths stored time-major [steps, vars,
+    paths] in HBM (output='device').  Kernel time = CUDA events around
+    sdeb_integrate on the launching stream (best of 3 after one warm-up)."""
+    from sdepy_b200 import _lib
+    peak, src = measured_hbm_peak()
+    events = []
+    real = _lib.lib.sdeb_integrate
+
+    def timed_integrate(p, stream):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = real(p, stream)
+        e1.record()
+        events.append((e0, e1))
+        return rc
+
+    def kernel_seconds(fn):
+        best = None
+        for it in range(4):
+            del events[:]
+            out = fn()
+            torch.cuda.synchronize(dev)
+            t = sum(e0.elapsed_time(e1) for e0, e1 in events)*1e-3
+            del out
+            if it and (best is None or t < best):
+                best = t
+        return best
+
+    def hw_theta(t):
+        return np.array(((.02 + .001*t,), (0.,), (0.,)))
+
+    def hw_corr(t):
+        c01, c02, c12 = .3*np.cos(t), -.2 + .05*t, .1
+        return np.array(((1, c01, c02), (c01, 1, c12), (c02, c12, 1)))
+
+    out = {}
+    _lib.lib.sdeb_integrate = timed_integrate
+    try:
+        p, n = 1_000_000, 500
+        tl = np.linspace(0., 5., n + 1)
+        cases = [
+            ('C2a_ou_tdep_philox', p, n, 0, lambda: sd.ornstein_uhlenbeck_process(
+                x0=.1, theta=lambda s: .2 + .1*s, k=1., sigma=.3, paths=p, seed=2,
+                output='device')(tl)),
+            ('C2b_hw3f_tdep_corr_philox', p, n, 0, lambda: sd.hull_white_process(
+                factors=3, x0=((.01,), (0.,), (0.,)), theta=hw_theta,
+                k=((.1,), (.5,), (1.,)), sigma=((.01,), (.008,), (.005,)), corr=hw_corr,
+                paths=p, seed=3, output='device')(tl))]
+        pr, nr = 4_000_000, 250
+        g = torch.Generator(device=dev)
+        g.manual_seed(0)
+        dW = torch.randn((nr, pr), dtype=torch.float64, device=dev, generator=g)*np.sqrt(1/nr)
+        tlr = np.linspace(0., 1., nr + 1)
+        cases.append(('replay_ou', pr, nr, pr*nr, lambda: sd.ornstein_uhlenbeck_process(
+            x0=.1, theta=.2, k=1., sigma=.3, paths=pr, dw=sd.replay_source(dW),
+            output='device')(tlr)))
+        for name, paths, steps, read, fn in cases:
+            t = kernel_seconds(fn)
+            nbytes = 8.*(paths*(steps + 1) + read)
+            out[name] = {'paths': paths, 'steps': steps, 'kernel_s': t,
+                         'path_steps_per_s': paths*steps/t,
+                         'algorithmic_bytes': nbytes, 'GBps': nbytes/t/1e9,
+                         'frac_of_hbm_peak': nbytes/t/1e9/peak}
+        del dW
+    finally:
+        _lib.lib.sdeb_integrate = real
+    out['hbm_peak_GBps'] = peak
+    out['hbm_peak_source'] = src
+    out['note'] = ('full-path output mode, stored rows [steps+1, paths] fp64 in HBM; '
+                   'algorithmic bytes = 8 B per stored value (+ 8 B per replayed increment); '
+                   'the Philox rows are FP64-issue bound (draws), replay_ou is the HBM-bound one')
+    return out
+
+
+def c5_allreduce_check(sd, torch, dist, rank, world, dev):
+    """BASELINE config 5, scaled: custom @integrate GBM, Milstein, 2e7 GLOBAL
+    paths x 2000 steps sharded over the ranks; histogram edges fixed by a first
+    min/max all-reduce (np.histogram's range=None rule, reference
+    infrastructure.py:2999-3004), then montecarlo(...).allreduce().  Rank 0
+    recomputes everything in one process and compares: counts and edges
+    array_equal, moments rtol 1e-10."""
+    from sdepy_b200.distributed import shard, allreduce_minmax
+    total, nsteps = 20_000_003, 2000
+
+    @sd.integrate
+    def gbm(t, x, mu=.05, sigma=.2):
+        return {'dt': mu*x, 'dw': sigma*x}
+
+    kw = dict(steps=nsteps + 1, x0=1., method='milstein', seed=12, output='device',
+              getinfo=False)
+    off, cnt = shard(total, rank, world)
+    x = gbm(paths=cnt, path_offset=off, **kw)((0., 1.))
+    lo, hi = float(np.asarray(x.pmin())[-1, 0]), float(np.asarray(x.pmax())[-1, 0])
+    lo, hi = allreduce_minmax(lo, hi)
+    mc = sd.montecarlo(x.x[-1], bins=100, range=(lo, hi))
+    if world > 1:
+        mc.allreduce()
+    else:
+        # one rank: cumulate the same paths in two chunks instead
+        half = cnt//2
+        mc = sd.montecarlo(x.x[-1][:half], bins=100, range=(lo, hi))
+        mc.update(x.x[-1][half:])
+    res = {'global_paths': total, 'steps': nsteps, 'ranks': world}
+    if rank == 0:
+        full = x if world == 1 else gbm(paths=total, **kw)((0., 1.))
+        ref = sd.montecarlo(full.x[-1], bins=100)
+        ok = mc.paths == total == ref.paths
+        ok = ok and np.array_equal(mc.histogram()[1], ref.histogram()[1])
+        ok = ok and np.array_equal(mc.histogram()[0], ref.histogram()[0])
+        ok = ok and int(mc.outpaths) == int(ref.outpaths) == 0
+        for f in ('mean', 'var', 'skew', 'kurtosis', 'stderr'):
+            ok = ok and bool(np.allclose(getattr(mc, f)(), getattr(ref, f)(), rtol=1e-10, atol=0))
+        res.update(ok=bool(ok), mean=float(mc.mean()), stderr=float(mc.stderr()),
+                   expected_mean=float(np.exp(.05)),
+                   histogram_total=int(mc.histogram()[0].sum()))
+    return res
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
     import sdepy_b200 as sd
     from sdepy_b200 import _engine, _lib, _cuda
+    from sdepy_b200.distributed import shard
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -230,68 +370,92 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def make(seed):
-        return sd.heston_process(paths=paths, steps=grid, rho=RHO, seed=seed,
+    def make(seed, npaths, offset):
+        return sd.heston_process(paths=npaths, steps=grid, rho=RHO, seed=seed,
                                  output='stats', payoff=payoff, getinfo=True,
-                                 path_offset=rank*paths, **HESTON)
+                                 path_offset=offset, **HESTON)
 
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
-    # ---- device-timed: tables resident, K launches ------------------------
-    res = _engine.resident_stats_run(make(1), timeline)
-    packed = torch.zeros(res.stats.numel() + 1, dtype=torch.float64, device=dev)
+    def measure(npaths, offset, sample_clocks):
+        """(device ms over K steps, e2e seconds over K steps, clocks, last sums,
+        last e2e price, kernels per step) for `npaths` local paths."""
+        # ---- device-timed: tables resident, K launches --------------------
+        res = _engine.resident_stats_run(make(1, npaths, offset), timeline)
+        packed = torch.zeros(res.stats.numel() + 1, dtype=torch.float64, device=dev)
 
-    def step_resident(i):
-        st = res.launch(0x5DEECE66D + i)
-        if world > 1:   # the path's only exchange: one all-reduce of the sums
-            packed[:-1] = st.reshape(-1)
-            dist.all_reduce(packed)
-        return st
+        def step_resident(i):
+            st = res.launch(0x5DEECE66D + i)
+            if world > 1:   # the path's only exchange: one all-reduce of the sums
+                packed[:-1] = st.reshape(-1)
+                dist.all_reduce(packed)
+            return st
 
-    for i in range(a.warmup):
-        step_resident(i)
-    barrier()
-    sampler = clock_sampler(local)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(a.steps)]
-    barrier()
+        for i in range(a.warmup):
+            step_resident(i)
+        barrier()
+        sampler = clock_sampler(local)
+        if sample_clocks and rank == 0:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(a.steps)]
+        barrier()
+        for i in range(a.steps):
+            flush.fill_(i & 0xff)                 # L2 flush, outside the event pair
+            ev[i][0].record()
+            st = step_resident(a.warmup + i)
+            ev[i][1].record()
+        barrier()
+        dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+        clocks = sampler.stop() if sample_clocks and rank == 0 else None
+        sums = st.cpu().numpy()
+        # ---- end to end through the public API ----------------------------
+        for i in range(max(2, a.warmup)):
+            r = make(100 + i, npaths, offset)(timeline)
+            if world > 1:
+                r = r.allreduce()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(a.steps):
+            r = make(200 + i, npaths, offset)(timeline)   # lowering + H2D + kernel + D2H
+            if world > 1:
+                r = r.allreduce()
+            price = float(np.asarray(r.payoff_mean())[-1, 0])
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), clocks, sums, price, res.kernels_per_launch
+
     wall0 = time.perf_counter()
-    for i in range(a.steps):
-        flush.fill_(i & 0xff)                     # L2 flush, outside the event pair
-        ev[i][0].record()
-        st = step_resident(a.warmup + i)
-        ev[i][1].record()
-    barrier()
+    dev_ms, e2e_s, clocks, sums, price, kpl = measure(paths, rank*paths, True)
     wall = time.perf_counter() - wall0
-    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
-    clocks = sampler.stop() if rank == 0 else None
-    sums = st.cpu().numpy()
 
-    # ---- end to end through the public API --------------------------------
-    for i in range(2):
-        r = make(100 + i)(timeline)
-        if world > 1:
-            r = r.allreduce()
+    # ---- strong scaling: the same 1e8 GLOBAL paths split over the ranks ----
+    strong = None
+    if world > 1:
+        off, cnt = shard(paths, rank, world)
+        s_ms, s_e2e, _, s_sums, s_price, _ = measure(cnt, off, False)
+        strong = {
+            'global_paths': paths, 'paths_per_gpu': paths//world,
+            'value': paths*N_STEPS*a.steps/(s_ms*1e-3), 'unit': 'path-steps/s',
+            'ms_per_step': s_ms/a.steps,
+            'e2e': paths*N_STEPS*a.steps/s_e2e, 'e2e_ms_per_step': 1e3*s_e2e/a.steps,
+            # this run's own single-GPU time for 1e8 paths is the weak line's step
+            'efficiency': dev_ms/(world*s_ms), 'e2e_efficiency': e2e_s/(world*s_e2e),
+            'e2e_call_price': s_price,
+            'note': 'same workload, %d GLOBAL paths sharded over %d ranks (one all-reduce '
+                    'of the sums per step); efficiency = T(1 GPU, %d paths, this run: the '
+                    'weak line) / (N x T(N GPUs))' % (paths, world, paths)}
+
+    # ---- the other configurations, under the same driver run ---------------
+    modes = full_path_modes(sd, torch, dev) if rank == 0 else None
     barrier()
-    t0 = time.perf_counter()
-    for i in range(a.steps):
-        r = make(200 + i)(timeline)               # lowering + H2D + kernel + D2H
-        if world > 1:
-            r = r.allreduce()
-        price = float(np.asarray(r.payoff_mean())[-1, 0])
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    c5 = c5_allreduce_check(sd, torch, dist, rank, world, dev)
     # per step: steps table, store rows, parameter record, initial state, centre
     h2d = N_STEPS*16 + N_STEPS*4 + 9*8 + 2*8 + 8
     d2h = 2*_lib.NSTAT*8
-
-    # ---- reduce timings over ranks ----------------------------------------
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s = float(t[0]), float(t[1])
 
     if rank == 0:
         total_steps = world*paths*N_STEPS*a.steps
@@ -301,8 +465,14 @@ def run_ours(a):
         _lib.check(_lib.lib.sdeb_fp64_peak(200_000, ctypes.byref(peak), _cuda.stream_ptr(dev)))
         peak_tf = peak.value*2/1e12
         per_gpu = value/world
+        cnt_ = load_counters()
+        n64 = cnt_['fp64_pipe_instr_per_path_step']
         achieved_tf = per_gpu*ALGO_FP64_INSTR_PER_PATH_STEP*2/1e12
-        executed_tf = per_gpu*N64_PER_PATH_STEP*2/1e12
+        executed_tf = per_gpu*n64*2/1e12
+        # issue-slot view: cycles one sub-partition spends per warp-step in THIS
+        # run (SM clock sampled under load) against the warp instructions it issues
+        sm_hz = 1e6*((clocks or {}).get('sm_mhz') or cnt_['sm_mhz'])
+        cyc = N_SMSP*sm_hz*32/per_gpu
         n = paths
         pay_mean = sums[-1, 0, 6]/n
         pay_se = float(np.sqrt(max(sums[-1, 0, 7]/n - pay_mean**2, 0)/(n - 1)))
@@ -314,30 +484,42 @@ def run_ours(a):
             'data': 'synthetic', 'config': config_of(paths, world),
             'e2e': {'value': total_steps/e2e_s, 'unit': 'path-steps/s',
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-            'gpu_launches': a.steps*res.kernels_per_launch,
+            'gpu_launches': a.steps*kpl,
             'clocks': clocks,
             'roofline': {
                 'bound': 'fp64', 'achieved': achieved_tf, 'peak': peak_tf,
                 'unit': 'TFLOP/s', 'frac': achieved_tf/peak_tf,
-                'traffic': int(NCU_DRAM_BYTES_PER_PATH*paths),
-                'executed': {'fp64_instr_per_path_step': N64_PER_PATH_STEP,
+                'traffic': int(cnt_['dram_bytes_per_path']*paths),
+                'executed': {'fp64_instr_per_path_step': n64,
                              'achieved': executed_tf, 'frac': executed_tf/peak_tf},
+                'issue': {'warp_instr_per_warp_step': cnt_['warp_instr_per_path_step'],
+                          'cycles_per_warp_step': cyc,
+                          'frac': cnt_['warp_instr_per_path_step']/cyc,
+                          'fp64_pipe_frac': 2*n64/cyc,
+                          'floor_cycles': max(cnt_['warp_instr_per_path_step'], 2*n64)},
+                'counters': {k: cnt_[k] for k in ('commit', 'source', 'command',
+                                                  'ncu_fp64_pipe_pct', 'ncu_issue_active_pct')},
                 'note': 'per GPU. achieved = ALGORITHMIC work (SURVEY 8d: %d FP64-pipe '
                         'instr per Heston path-step with libdevice transcendental '
                         'costs) x path-steps/s x 2 flop; peak = DFMA rate measured '
                         'live by sdeb_fp64_peak (MEASURED_PEAKS.json holds no FP64 '
-                        'figure). "executed" is the FP64-pipe utilisation of the '
-                        'instructions this kernel really issues (%d per path-step: '
-                        'its log/sqrt/sincos are hand-rolled), = ncu '
-                        'sm__pipe_fp64_cycles_active; frac can exceed 1 because '
-                        'the SURVEY figure prices the transcendentals at libdevice '
-                        'cost, which this kernel undercuts -- "executed" is the '
-                        'utilisation to read'
-                        % (ALGO_FP64_INSTR_PER_PATH_STEP, N64_PER_PATH_STEP)},
+                        'figure); frac exceeds 1 because the kernel\'s hand-rolled '
+                        'log/sqrt/sincos undercut the libdevice pricing. "executed" = '
+                        'FP64-pipe utilisation of the instructions really issued (%.1f '
+                        'per path-step, ncu counters of the named commit; = ncu '
+                        'sm__pipe_fp64_cycles_active). "issue" = warp instructions per '
+                        'warp-step / cycles a sub-partition spends per warp-step in this '
+                        'run (= ncu smsp__issue_active): the fraction to read, < 1 by '
+                        'construction; floor_cycles = max(issue slots, 2 x FP64 instr)'
+                        % (ALGO_FP64_INSTR_PER_PATH_STEP, n64)},
             'check': {'call_price_last_step': pay_mean, 'stderr': pay_se,
-                      'closed_form': 9.2425, 'e2e_price': price},
+                      'closed_form': 9.2425, 'e2e_price': price,
+                      'c5_allreduce_ok': c5.get('ok'), 'c5': c5},
+            'modes': modes,
             'wall_s_timed_region': wall,
         }
+        if strong is not None:
+            out['strong'] = strong
         if not a.no_cpu_baseline:
             out['cpu_baseline'] = cpu_baseline(a.cpu_sample_paths)
         print(json.dumps(out))

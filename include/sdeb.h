@@ -184,6 +184,37 @@ int sdeb_moments(const double* x, int64_t n_rows, int64_t n_paths, int64_t pitch
                  double* stats, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * montecarlo in two HBM passes (montecarlo.update, infrastructure.py:2869-3021).
+ *  sdeb_mc_range : pass 1 of the FIRST sample -- stats[row] = {sum, 0, 0, 0, min,
+ *      max, 0, 0}: the centring constant (first-sample mean, 2934) and the
+ *      histogram range of numpy.histogram(range=None) (2999-3004).
+ *  sdeb_mc_update : ONE pass giving the power sums S1..S4 of (x - centre)
+ *      (stats[row][0..3], 2940-2946) AND the histogram (counts/outside are
+ *      ACCUMULATED, 3010-3013), every row with its own edges[row][nbins+1].
+ *      centre == NULL: centre = range_stats[row][0] / n.
+ *      edges_mode SDEB_MC_EDGES_GIVEN: edges are read; _MINMAX / _RANGE: edges are
+ *      BUILT on the device exactly as numpy.linspace(lo, hi, nbins + 1) does
+ *      (step = (hi - lo)/nbins, e_i = fl(fl(i*step) + lo), e_nbins = hi; lo == hi
+ *      widens by 1/2 each side) from the min/max of range_stats or from
+ *      (range_lo, range_hi), and written back to `edges` -- no host round trip
+ *      between the two passes.  nbins == 0: moments only.
+ *  workspace >= sdeb_moments_workspace(n_rows) bytes for both.
+ */
+#define SDEB_MC_EDGES_GIVEN  0
+#define SDEB_MC_EDGES_MINMAX 1
+#define SDEB_MC_EDGES_RANGE  2
+int sdeb_mc_range(const double* x, int64_t n_rows, int64_t n, int64_t pitch, double* stats,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+int sdeb_mc_update(const double* x, int64_t n_rows, int64_t n, int64_t pitch,
+                   const double* centre /* [n_rows] device or NULL */,
+                   const double* range_stats /* [n_rows][SDEB_NSTAT] device or NULL */,
+                   double range_lo, double range_hi, int64_t edges_mode,
+                   double* edges /* [n_rows][nbins+1] device */, int64_t nbins,
+                   int64_t uniform_edges, double* stats /* [n_rows][SDEB_NSTAT] */,
+                   int64_t* counts /* [n_rows][nbins] */, int64_t* outside /* [n_rows] */,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Antithetic halves: out[r][k] = (x[r][k] + sign*x[r][half+k])/2, sign = +1 ('even')
  * or -1 ('odd') -- montecarlo(use=...), infrastructure.py:2905-2914.
  */

@@ -120,8 +120,7 @@ def moments(x2d, n_paths, centre=None):
     for r0 in range(0, rows, 32768):
         r1 = min(rows, r0 + 32768)
         n = r1 - r0
-        ws_bytes = _lib.lib.sdeb_moments_workspace(n)
-        ws = empty((ws_bytes // 8,), dev)
+        ws, ws_bytes = _workspace(n, dev)
         stats = empty((n, _lib.NSTAT), dev)
         c = None
         if centre is not None:
@@ -142,3 +141,40 @@ def histogram(x1d, edges, counts, outside, uniform):
         _lib.check(_lib.lib.sdeb_histogram(
             ptr(x1d), x1d.numel(), ptr(e), len(edges) - 1, int(bool(uniform)),
             ptr(counts), ptr(outside), stream_ptr(dev)))
+
+
+def _workspace(rows, dev):
+    nbytes = _lib.lib.sdeb_moments_workspace(rows)
+    return empty((nbytes // 8,), dev), nbytes
+
+
+def mc_range(x2d, n):
+    """Pass 1 of montecarlo's first update (sdeb_mc_range): device tensor
+    [rows, NSTAT] holding sum (slot 0), min (4), max (5) of every row.  No
+    host synchronisation."""
+    dev = x2d.device
+    rows, pitch = x2d.shape
+    stats = empty((rows, _lib.NSTAT), dev)
+    ws, ws_bytes = _workspace(rows, dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.sdeb_mc_range(ptr(x2d), rows, n, pitch, ptr(stats), ptr(ws),
+                                          ws_bytes, stream_ptr(dev)))
+    return stats
+
+
+def mc_update(x2d, n, *, centre=None, range_stats=None, lo=0., hi=0.,
+              edges_mode=_lib.MC_EDGES_GIVEN, edges=None, nbins=0, uniform=True,
+              counts=None, outside=None):
+    """Fused moments + histogram pass (sdeb_mc_update) over the rows of x2d;
+    all arrays are device tensors, the result is the device tensor
+    [rows, NSTAT] of centred power sums.  No host synchronisation."""
+    dev = x2d.device
+    rows, pitch = x2d.shape
+    stats = empty((rows, _lib.NSTAT), dev)
+    ws, ws_bytes = _workspace(rows, dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.sdeb_mc_update(
+            ptr(x2d), rows, n, pitch, ptr(centre), ptr(range_stats), float(lo), float(hi),
+            int(edges_mode), ptr(edges), int(nbins), int(bool(uniform)), ptr(stats),
+            ptr(counts), ptr(outside), ptr(ws), ws_bytes, stream_ptr(dev)))
+    return stats

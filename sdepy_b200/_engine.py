@@ -126,7 +126,8 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
         # (integration.py:550)
         res.out.fill_(float('nan'))
     res.stats = None
-    res.counter = (_cuda.zeros((spec.groups*spec.ncnt, paths), dev, torch.int64)
+    # (zeroed at the start of every sweep, below)
+    res.counter = (_cuda.empty((spec.groups*spec.ncnt, paths), dev, torch.int64)
                    if counters and spec.ncnt else None)
     res.dn_sum, res.dump = [], []
     stats_total = None

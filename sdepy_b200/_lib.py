@@ -69,6 +69,9 @@ def _load():
     lib.sdeb_integrate.argtypes = [C.POINTER(Problem), ptr]
     lib.sdeb_moments.argtypes = [ptr, i64, i64, i64, ptr, ptr, ptr, i64, ptr]
     lib.sdeb_histogram.argtypes = [ptr, i64, ptr, i64, i64, ptr, ptr, ptr]
+    lib.sdeb_mc_range.argtypes = [ptr, i64, i64, i64, ptr, ptr, i64, ptr]
+    lib.sdeb_mc_update.argtypes = [ptr, i64, i64, i64, ptr, ptr, f64, f64, i64, ptr, i64, i64,
+                                   ptr, ptr, ptr, ptr, i64, ptr]
     lib.sdeb_path_eval_workspace.restype = i64
     lib.sdeb_path_eval_workspace.argtypes = [i64]
     lib.sdeb_path_cdf.argtypes = [ptr, ptr, f64, f64, i64, i64, ptr, i64, ptr, ptr]
@@ -97,13 +100,14 @@ lib = _load()
 
 EXPORTS = ('sdeb_abi_version', 'sdeb_last_error', 'sdeb_device_info',
            'sdeb_plan', 'sdeb_integrate', 'sdeb_moments_workspace',
-           'sdeb_moments', 'sdeb_histogram', 'sdeb_antithetic_fold', 'sdeb_path_eval_workspace', 'sdeb_path_cdf',
+           'sdeb_moments', 'sdeb_histogram', 'sdeb_mc_range', 'sdeb_mc_update', 'sdeb_antithetic_fold', 'sdeb_path_eval_workspace', 'sdeb_path_cdf',
            'sdeb_path_chf', 'sdeb_path_interp', 'sdeb_axis_reduce', 'sdeb_time_scan', 'sdeb_draw_wiener', 'sdeb_bridge_wiener',
            'sdeb_draw_cpoisson', 'sdeb_test_normals', 'sdeb_test_philox',
            'sdeb_fp64_peak', 'sdeb_jit_compile', 'sdeb_jit_release')
 
 
 SCAN_CUMSUM, SCAN_INT, SCAN_DIFF = 0, 1, 2
+MC_EDGES_GIVEN, MC_EDGES_MINMAX, MC_EDGES_RANGE = 0, 1, 2
 
 
 def check(rc):

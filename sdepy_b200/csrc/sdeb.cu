@@ -272,25 +272,36 @@ extern "C" int sdeb_integrate(const sdeb_problem* p, void* stream_) {
 // ---------------------------------------------------------------------------
 // across-path statistics of stored rows
 // ---------------------------------------------------------------------------
-static const int kMomBlocks = 296;   // per row: 2 x 148 SMs
-
-__global__ void __launch_bounds__(256)
-moments_kernel(const double* x, int64_t n_paths, int64_t pitch, const double* centre,
-               double* partials) {
-    const int row = blockIdx.y;
-    const double c = centre ? centre[row] : 0.0;
-    const double* xr = x + (int64_t)row * pitch;
-    double st[NSTAT];
-    st[0] = st[1] = st[2] = st[3] = st[6] = st[7] = 0.0;
-    st[4] = __longlong_as_double(0x7FF0000000000000LL);
-    st[5] = __longlong_as_double(0xFFF0000000000000LL);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_paths;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        double v = xr[i];
-        double d = v - c, d2 = d * d;
-        st[0] += d; st[1] += d2; st[2] += d2 * d; st[3] += d2 * d2;
-        st[4] = fmin(st[4], v); st[5] = fmax(st[5], v);
+// Streaming reader of one row: 16-byte loads, four independent loads in flight
+// per thread (8 CTAs x 256 threads x 64 B = 128 KB per SM: HBM latency x
+// bandwidth needs ~45 KB), evict-first.  f(v) is applied to every element
+// exactly once; which thread sees which element is fixed by the launch
+// geometry, so the block partials -- folded in block order -- are reproducible.
+template <class F>
+__device__ __forceinline__ void stream_row(const double* __restrict__ xr, int64_t n, F&& f) {
+    const int64_t head = ((((uintptr_t)xr) & 15) != 0 && n > 0) ? 1 : 0;
+    const int64_t nvec = (n - head) >> 1;
+    const double2* __restrict__ xv = (const double2*)(xr + head);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = tid;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        const double2 a = __ldcs(xv + i), b = __ldcs(xv + i + stride);
+        const double2 c = __ldcs(xv + i + 2 * stride), d = __ldcs(xv + i + 3 * stride);
+        f(a.x); f(a.y); f(b.x); f(b.y); f(c.x); f(c.y); f(d.x); f(d.y);
     }
+    for (; i < nvec; i += stride) {
+        const double2 a = __ldcs(xv + i);
+        f(a.x); f(a.y);
+    }
+    if (tid == 0) {
+        if (head) f(xr[0]);
+        if ((n - head) & 1) f(xr[n - 1]);
+    }
+}
+
+// block reduction of one NSTAT vector -> partials[block][row][NSTAT]
+__device__ __forceinline__ void block_fold_stats(double (&st)[NSTAT], double* partials, int row) {
     __shared__ double s_warp[8][NSTAT];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -318,23 +329,209 @@ moments_kernel(const double* x, int64_t n_paths, int64_t pitch, const double* ce
     }
 }
 
-extern "C" int64_t sdeb_moments_workspace(int64_t n_rows) {
-    return (int64_t)kMomBlocks * n_rows * NSTAT * 8;
+// RANGE_ONLY: sum, min, max (pass 1 of montecarlo's first update: the centring
+// constant and the histogram range); else S1..S4 about `centre`, min, max
+template <bool RANGE_ONLY>
+__global__ void __launch_bounds__(256)
+moments_kernel(const double* x, int64_t n_paths, int64_t pitch, const double* centre,
+               double* partials) {
+    const int row = blockIdx.y;
+    const double c = centre ? centre[row] : 0.0;
+    const double* xr = x + (int64_t)row * pitch;
+    double st[NSTAT];
+    st[0] = st[1] = st[2] = st[3] = st[6] = st[7] = 0.0;
+    st[4] = __longlong_as_double(0x7FF0000000000000LL);
+    st[5] = __longlong_as_double(0xFFF0000000000000LL);
+    stream_row(xr, n_paths, [&](double v) {
+        if (RANGE_ONLY) {
+            st[0] += v;
+        } else {
+            double d = v - c, d2 = d * d;
+            st[0] += d; st[1] += d2; st[2] = fma(d2, d, st[2]); st[3] = fma(d2, d2, st[3]);
+        }
+        st[4] = fmin(st[4], v); st[5] = fmax(st[5], v);
+    });
+    block_fold_stats(st, partials, row);
 }
 
-extern "C" int sdeb_moments(const double* x, int64_t n_rows, int64_t n_paths, int64_t pitch,
-                            const double* centre, double* stats, void* workspace,
-                            int64_t workspace_bytes, void* stream_) {
+// grid.x per row: ~8 resident CTAs per SM over all rows, at least 2 per row
+static int64_t mom_blocks(int64_t n_rows, int64_t n) {
+    int64_t per = 1184 / n_rows;
+    if (per < 2) per = 2;
+    int64_t need = (n + 2047) / 2048;
+    if (need < 1) need = 1;
+    return need < per ? need : per;
+}
+
+extern "C" int64_t sdeb_moments_workspace(int64_t n_rows) {
+    if (n_rows < 1) n_rows = 1;
+    int64_t per = 1184 / n_rows;
+    if (per < 2) per = 2;
+    return per * n_rows * NSTAT * 8;
+}
+
+static int moments_impl(bool range_only, const double* x, int64_t n_rows, int64_t n_paths,
+                        int64_t pitch, const double* centre, double* stats, void* workspace,
+                        int64_t workspace_bytes, void* stream_) {
     if (!x || !stats || n_rows < 1 || n_paths < 1 || pitch < n_paths)
         return fail(SDEB_EINVAL, "sdeb_moments: bad arguments");
     if (n_rows > 65535) return fail(SDEB_EINVAL, "sdeb_moments: n_rows > 65535 (chunk the rows)");
     if (!workspace || workspace_bytes < sdeb_moments_workspace(n_rows))
         return fail(SDEB_EINVAL, "sdeb_moments: workspace too small");
     cudaStream_t stream = (cudaStream_t)stream_;
-    int64_t need = (n_paths + 255) / 256;
-    int blocks = (int)(need < kMomBlocks ? need : kMomBlocks);
-    moments_kernel<<<dim3(blocks, (unsigned)n_rows), 256, 0, stream>>>(
-        x, n_paths, pitch, centre, (double*)workspace);
+    const int blocks = (int)mom_blocks(n_rows, n_paths);
+    if (range_only)
+        moments_kernel<true><<<dim3(blocks, (unsigned)n_rows), 256, 0, stream>>>(
+            x, n_paths, pitch, NULL, (double*)workspace);
+    else
+        moments_kernel<false><<<dim3(blocks, (unsigned)n_rows), 256, 0, stream>>>(
+            x, n_paths, pitch, centre, (double*)workspace);
+    CUDA_TRY(cudaGetLastError());
+    int64_t len = n_rows * NSTAT;
+    fold_partials_kernel<<<(unsigned)((len * 32 + 127) / 128), 128, 0, stream>>>(
+        (const double*)workspace, blocks, len, stats);
+    CUDA_TRY(cudaGetLastError());
+    return SDEB_OK;
+}
+
+extern "C" int sdeb_moments(const double* x, int64_t n_rows, int64_t n_paths, int64_t pitch,
+                            const double* centre, double* stats, void* workspace,
+                            int64_t workspace_bytes, void* stream_) {
+    return moments_impl(false, x, n_rows, n_paths, pitch, centre, stats, workspace,
+                        workspace_bytes, stream_);
+}
+
+extern "C" int sdeb_mc_range(const double* x, int64_t n_rows, int64_t n, int64_t pitch,
+                             double* stats, void* workspace, int64_t workspace_bytes,
+                             void* stream_) {
+    return moments_impl(true, x, n_rows, n, pitch, NULL, stats, workspace, workspace_bytes,
+                        stream_);
+}
+
+// ---------------------------------------------------------------------------
+// montecarlo update in ONE pass over the sample (reference infrastructure.py:
+// 2924-3021): centred power sums S1..S4 AND the histogram of every row.
+//  * centre: given, or sum/n of the range pass (first sample, 2934)
+//  * edges : given, or built here exactly as numpy.linspace(lo, hi, nbins + 1)
+//            does for numpy.histogram(range=None | (lo, hi)) (2999-3004):
+//            step = (hi - lo)/nbins, e_i = fl(fl(i*step) + lo), e_nbins = hi;
+//            lo == hi widens to (lo - 1/2, hi + 1/2)
+//  * bins  : numpy.histogram semantics (half-open, last closed), arithmetic
+//            guess + edge fix-up against the edges in shared memory; counts in
+//            WARP-PRIVATE 32-bit shared counters (one atomic per element hits
+//            only the lanes of its own warp that share the bin), flushed with
+//            64-bit global atomics -- integer, hence order-independent.
+// ---------------------------------------------------------------------------
+enum { MC_EDGES_GIVEN = 0, MC_EDGES_MINMAX = 1, MC_EDGES_RANGE = 2 };
+
+__global__ void __launch_bounds__(256)
+mc_update_kernel(const double* x, int64_t n, int64_t pitch, const double* centre,
+                 const double* range_stats, double range_lo, double range_hi, int edges_mode,
+                 double* edges, int nbins, int uniform, int copies,
+                 double* partials, unsigned long long* counts, unsigned long long* outside) {
+    extern __shared__ double sh[];
+    const int row = blockIdx.y;
+    double* s_edges = sh;                                       // nbins + 1
+    unsigned int* s_cnt = (unsigned int*)(sh + nbins + 1);      // copies x (nbins + 1)
+    const int cstride = nbins + 1;                              // last slot: outside
+    const double* xr = x + (int64_t)row * pitch;
+    const double c = centre ? centre[row] : __ddiv_rn(range_stats[row * NSTAT], (double)n);
+    if (nbins > 0) {
+        double* e = edges + (int64_t)row * (nbins + 1);
+        if (edges_mode == MC_EDGES_GIVEN) {
+            for (int i = threadIdx.x; i <= nbins; i += blockDim.x) s_edges[i] = e[i];
+        } else {
+            double lo = range_lo, hi = range_hi;
+            if (edges_mode == MC_EDGES_MINMAX) {
+                lo = range_stats[row * NSTAT + 4]; hi = range_stats[row * NSTAT + 5];
+                // a NaN in the sample poisons the sum: numpy's range is then NaN
+                if (range_stats[row * NSTAT] != range_stats[row * NSTAT]) lo = hi = range_stats[row * NSTAT];
+            }
+            if (lo == hi) { lo = __dsub_rn(lo, 0.5); hi = __dadd_rn(hi, 0.5); }
+            const double step = __ddiv_rn(__dsub_rn(hi, lo), (double)nbins);
+            for (int i = threadIdx.x; i <= nbins; i += blockDim.x) {
+                double v = (i == nbins) ? hi : __dadd_rn(__dmul_rn((double)i, step), lo);
+                s_edges[i] = v;
+                if (blockIdx.x == 0) e[i] = v;
+            }
+        }
+        for (int i = threadIdx.x; i < copies * cstride; i += blockDim.x) s_cnt[i] = 0;
+    }
+    __syncthreads();
+    const double lo = nbins > 0 ? s_edges[0] : 0.0, hi = nbins > 0 ? s_edges[nbins] : 0.0;
+    const double scale = nbins / (hi - lo);
+    unsigned int* my_cnt = s_cnt + ((threadIdx.x >> 5) % copies) * cstride;
+    double st[NSTAT];
+    st[0] = st[1] = st[2] = st[3] = st[6] = st[7] = 0.0;
+    st[4] = __longlong_as_double(0x7FF0000000000000LL);
+    st[5] = __longlong_as_double(0xFFF0000000000000LL);
+    stream_row(xr, n, [&](double v) {
+        double d = v - c, d2 = d * d;
+        st[0] += d; st[1] += d2; st[2] = fma(d2, d, st[2]); st[3] = fma(d2, d2, st[3]);
+        if (nbins > 0) {
+            int idx;
+            if (!(v >= lo && v <= hi)) {
+                idx = nbins;                                    // outside (or NaN)
+            } else {
+                if (uniform) {
+                    idx = (int)((v - lo) * scale);
+                    idx = idx < 0 ? 0 : (idx > nbins - 1 ? nbins - 1 : idx);
+                } else {
+                    int a = 0, b = nbins;                       // largest idx with edges[idx] <= v
+                    while (b - a > 1) { int m = (a + b) >> 1; if (s_edges[m] <= v) a = m; else b = m; }
+                    idx = a;
+                }
+                while (idx > 0 && v < s_edges[idx]) --idx;
+                while (idx < nbins - 1 && v >= s_edges[idx + 1]) ++idx;
+            }
+            atomicAdd(&my_cnt[idx], 1u);
+        }
+    });
+    block_fold_stats(st, partials, row);
+    if (nbins > 0) {
+        __syncthreads();
+        for (int i = threadIdx.x; i <= nbins; i += blockDim.x) {
+            unsigned int t = 0;
+            for (int k = 0; k < copies; ++k) t += s_cnt[k * cstride + i];
+            if (t) atomicAdd(i < nbins ? &counts[(int64_t)row * nbins + i] : &outside[row],
+                             (unsigned long long)t);
+        }
+    }
+}
+
+extern "C" int sdeb_mc_update(const double* x, int64_t n_rows, int64_t n, int64_t pitch,
+                              const double* centre, const double* range_stats,
+                              double range_lo, double range_hi, int64_t edges_mode,
+                              double* edges, int64_t nbins, int64_t uniform_edges,
+                              double* stats, int64_t* counts, int64_t* outside,
+                              void* workspace, int64_t workspace_bytes, void* stream_) {
+    if (!x || !stats || n_rows < 1 || n_rows > 65535 || n < 1 || pitch < n || nbins < 0)
+        return fail(SDEB_EINVAL, "sdeb_mc_update: bad arguments");
+    if (!centre && !range_stats)
+        return fail(SDEB_EINVAL, "sdeb_mc_update: needs a centre or the statistics of the range pass");
+    if (nbins > 0) {
+        if (!edges || !counts || !outside)
+            return fail(SDEB_EINVAL, "sdeb_mc_update: histogram buffers are NULL");
+        if (nbins > 4000) return fail(SDEB_EINVAL, "sdeb_mc_update: at most 4000 bins");
+        if (edges_mode < MC_EDGES_GIVEN || edges_mode > MC_EDGES_RANGE ||
+            (edges_mode == MC_EDGES_MINMAX && !range_stats))
+            return fail(SDEB_EINVAL, "sdeb_mc_update: bad edges_mode");
+    }
+    if (!workspace || workspace_bytes < sdeb_moments_workspace(n_rows))
+        return fail(SDEB_EINVAL, "sdeb_mc_update: workspace too small");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int blocks = (int)mom_blocks(n_rows, n);
+    // warp-private counter copies: as many as fit ~24 KB (8 CTAs per SM stay resident)
+    int copies = nbins > 0 ? (int)(24 * 1024 / (4 * (nbins + 1))) : 1;
+    copies = copies < 1 ? 1 : (copies > 8 ? 8 : copies);
+    size_t smem = nbins > 0 ? (size_t)(nbins + 1) * (8 + 4 * copies) : 0;
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(mc_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    mc_update_kernel<<<dim3(blocks, (unsigned)n_rows), 256, smem, stream>>>(
+        x, n, pitch, centre, range_stats, range_lo, range_hi, (int)edges_mode, edges, (int)nbins,
+        (int)uniform_edges, copies, (double*)workspace, (unsigned long long*)counts,
+        (unsigned long long*)outside);
     CUDA_TRY(cudaGetLastError());
     int64_t len = n_rows * NSTAT;
     fold_partials_kernel<<<(unsigned)((len * 32 + 127) / 128), 128, 0, stream>>>(

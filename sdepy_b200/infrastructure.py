@@ -1581,30 +1581,135 @@ class montecarlo:
         rows = x.reshape(-1, m)
         first = self.paths == 0
         n = self.paths
+        nrow = rows.shape[0]
         if first:
             # reference 2928-2930: a floating sample sets the dtype of the results
             dtype = ((sdtype if sdtype.kind == 'f' else float) if self.dtype is None
                      else self.dtype)
+            # pass 1 (sum, min, max): centring constant = first-sample mean
+            # (2934) and the range of numpy.histogram(range=None) (2999-3004)
+            rstats = torch.cat([_cuda.mc_range(rows[r0:r1], m)
+                                for r0, r1 in self._row_chunks(nrow)])
+            bins = self._bins
+            int_bins = isinstance(bins, (int, np.integer)) and not isinstance(bins, bool)
+            if np.dtype(dtype) == np.dtype(float) and (bins is None or int_bins):
+                # pass 2 builds centre and edges on the device from pass 1's
+                # result: no host round trip between the two passes
+                nb = 0 if bins is None else int(bins)
+                if bins is not None and nb < 1:
+                    raise ValueError('`bins` must be positive, when an integer')
+                mode, a, b = _lib.MC_EDGES_MINMAX, 0., 0.
+                if self._range is not None and nb:
+                    a, b = map(float, self._range)
+                    if a > b:
+                        raise ValueError('max must be larger than min in range parameter.')
+                    if not (np.isfinite(a) and np.isfinite(b)):
+                        raise ValueError('supplied range of [{}, {}] is not finite'.format(a, b))
+                    mode = _lib.MC_EDGES_RANGE
+                groups = self._alloc_groups([nb]*nrow, [True]*nrow, rows.device)
+                st = self._launch(groups, rows, m, None, rstats, mode, a, b)
+                rs = rstats.cpu().numpy()
+                st = st.cpu().numpy()
+                if nb and mode == _lib.MC_EDGES_MINMAX:
+                    for i in range(nrow):
+                        # a NaN anywhere in the sample makes numpy's range NaN
+                        lo_i, hi_i = ((np.nan, np.nan) if np.isnan(rs[i, 0])
+                                      else (rs[i, 4], rs[i, 5]))
+                        if not (np.isfinite(lo_i) and np.isfinite(hi_i)):
+                            raise ValueError('autodetected range of [{}, {}] is not finite'
+                                             .format(lo_i, hi_i))
+                center = (rs[:, 0]/m).reshape(vshape)
+                self._groups = groups
+                self._center_dev = _cuda.to_device(center.ravel(), rows.device)
+                if nb:
+                    self._edges, self._uniform = [], [True]*nrow
+                    for g in groups:
+                        e = g['edges'].cpu().numpy()
+                        self._edges += [e[i] for i in range(e.shape[0])]
+                    self._bins = np.empty(vshape, dtype=object)
+                    for j, i in enumerate(np.ndindex(vshape)):
+                        self._bins[i] = self._edges[j]
+            else:
+                rs = rstats.cpu().numpy()
+                center = (rs[:, 0]/m).reshape(vshape).astype(dtype)
+                lo, hi = rs[:, 4], rs[:, 5]
+                self._center_dev = _cuda.to_device(
+                    np.asarray(center, dtype=float).ravel(), rows.device)
+                centred = None
+                if isinstance(bins, str):
+                    # named estimators need the centred moments of the sample
+                    g0 = self._alloc_groups([0]*nrow, [True]*nrow, rows.device)
+                    centred = self._launch(g0, rows, m, self._center_dev).cpu().numpy()
+                if bins is not None:
+                    self._setup_bins(vshape, lo, hi, rows=rows, m=m, centred=centred,
+                                     integer=np.issubdtype(
+                                         getattr(sample, 'dtype', np.dtype(float))
+                                         if isinstance(sample, np.ndarray) else float,
+                                         np.integer))
+                else:
+                    self._groups = self._alloc_groups([0]*nrow, [True]*nrow, rows.device)
+                st = self._launch(self._groups, rows, m, self._center_dev).cpu().numpy()
+            self._center = center
             self._moments = tuple(np.zeros(vshape, dtype=dtype) for _ in range(4))
             self._mean = np.zeros(vshape, dtype=dtype)
-            pass1 = _cuda.moments(rows, m)
-            self._center = (pass1[:, 0]/m).reshape(vshape).astype(dtype)
-            lo, hi = pass1[:, 4], pass1[:, 5]
-        st = _cuda.moments(rows, m, centre=self._center.reshape(-1))
+        else:
+            if vshape != self.vshape:
+                raise ValueError('sample of shape {} incompatible with the shape {} of '
+                                 'the cumulated data'.format(vshape, self.vshape))
+            st = self._launch(self._groups, rows, m, self._center_dev).cpu().numpy()
         for k in range(4):
             mk = (st[:, k]/m).reshape(vshape)
             self._moments[k][...] = (n*self._moments[k] + m*mk)/(n + m)
         smean = self._center + (st[:, 0]/m).reshape(vshape)
         self._mean[...] = (n*self._mean + m*smean)/(n + m)
         if self._bins is not None:
-            if first:
-                self._setup_bins(vshape, lo, hi, rows=rows, m=m, centred=st,
-                                 integer=np.issubdtype(
-                                     getattr(sample, 'dtype', np.dtype(float))
-                                     if isinstance(sample, np.ndarray) else float,
-                                     np.integer))
-            self._update_histogram(rows, m)
+            self._read_histogram(m)
         self._paths[0] += m
+
+    @staticmethod
+    def _row_chunks(nrow, width=32768):
+        return [(r0, min(nrow, r0 + width)) for r0 in range(0, nrow, width)]
+
+    def _alloc_groups(self, nbins, uniform, dev, edges=None):
+        """Partition the rows into runs sharing (nbins, uniform) -- one fused
+        launch each -- and allocate their device edges / int64 counters."""
+        groups, r0, nrow = [], 0, len(nbins)
+        while r0 < nrow:
+            r1 = r0 + 1
+            while (r1 < nrow and r1 - r0 < 32768 and nbins[r1] == nbins[r0]
+                   and uniform[r1] == uniform[r0]):
+                r1 += 1
+            nb, k = int(nbins[r0]), r1 - r0
+            g = dict(r0=r0, r1=r1, nbins=nb, uniform=bool(uniform[r0]), edges=None,
+                     counts=None, outside=None)
+            if nb:
+                g['edges'] = (_cuda.empty((k, nb + 1), dev) if edges is None else
+                              _cuda.to_device(np.stack(edges[r0:r1]), dev, dtype=float))
+                g['counts'] = _cuda.zeros((k, nb), dev, torch.int64)
+                g['outside'] = _cuda.zeros((k,), dev, torch.int64)
+            groups.append(g)
+            r0 = r1
+        # per-row views (montecarlo.allreduce writes the merged counts back)
+        self._counts_dev = [g['counts'][i] for g in groups if g['nbins']
+                            for i in range(g['r1'] - g['r0'])]
+        self._outside_dev = [g['outside'][i:i + 1] for g in groups if g['nbins']
+                             for i in range(g['r1'] - g['r0'])]
+        return groups
+
+    @staticmethod
+    def _launch(groups, rows, m, centre_dev, rstats=None, mode=_lib.MC_EDGES_GIVEN,
+                lo=0., hi=0.):
+        """One fused moments + histogram launch per group; device [rows, NSTAT]."""
+        out = []
+        for g in groups:
+            r0, r1 = g['r0'], g['r1']
+            out.append(_cuda.mc_update(
+                rows[r0:r1], m,
+                centre=None if centre_dev is None else centre_dev[r0:r1],
+                range_stats=None if rstats is None else rstats[r0:r1],
+                lo=lo, hi=hi, edges_mode=mode, edges=g['edges'], nbins=g['nbins'],
+                uniform=g['uniform'], counts=g['counts'], outside=g['outside']))
+        return out[0] if len(out) == 1 else torch.cat(out)
 
     @staticmethod
     def _bin_width(name, row, n, a, b, mom, integer):
@@ -1663,6 +1768,7 @@ class montecarlo:
     def _setup_bins(self, vshape, lo, hi, rows=None, m=0, centred=None, integer=False):
         bins = self._bins
         nrow = int(np.prod(vshape, dtype=int))
+        dev = rows.device if rows is not None else _cuda.device(self._device)
         self._edges, self._uniform = [], []
         if isinstance(bins, str):
             for i in range(nrow):
@@ -1715,27 +1821,28 @@ class montecarlo:
                     raise ValueError('`bins` must increase monotonically, when an array')
                 self._edges.append(e)
                 self._uniform.append(False)
-        dev = _cuda.device(self._device)
-        self._counts_dev = [_cuda.zeros((len(e) - 1,), dev, torch.int64) for e in self._edges]
-        self._outside_dev = [_cuda.zeros((1,), dev, torch.int64) for _ in self._edges]
+        self._groups = self._alloc_groups([len(e) - 1 for e in self._edges], self._uniform,
+                                          dev, edges=self._edges)
         self._bins = np.empty(vshape, dtype=object)
         for j, i in enumerate(np.ndindex(vshape)):
             self._bins[i] = self._edges[j]
 
-    def _update_histogram(self, rows, m):
-        for j, e in enumerate(self._edges):
-            _cuda.histogram(rows[j], e, self._counts_dev[j], self._outside_dev[j],
-                            self._uniform[j])
+    def _read_histogram(self, m):
+        """Host copies of the cumulated counts (one D2H per launch group)."""
         vshape = self.vshape
         self._counts = np.empty(vshape, dtype=object)
         self._paths_outside = np.zeros(vshape, dtype=self.ctype)
-        for j, i in enumerate(np.ndindex(vshape)):
-            self._counts[i] = self._counts_dev[j].cpu().numpy().astype(self.ctype, copy=False)
-            self._paths_outside[i] = int(self._outside_dev[j].item())
-            if self._counts[i].sum() + self._paths_outside[i] != self.paths + m:
-                raise RuntimeError(
-                    'total number of cumulated paths inconsistent with stored '
-                    'cumulated counts')
+        index = list(np.ndindex(vshape))
+        for g in self._groups:
+            c, o = g['counts'].cpu().numpy(), g['outside'].cpu().numpy()
+            for k in range(g['r1'] - g['r0']):
+                i = index[g['r0'] + k]
+                self._counts[i] = c[k].astype(self.ctype, copy=False)
+                self._paths_outside[i] = int(o[k])
+                if self._counts[i].sum() + self._paths_outside[i] != self.paths + m:
+                    raise RuntimeError(
+                        'total number of cumulated paths inconsistent with stored '
+                        'cumulated counts')
 
     def allreduce(self, group=None):
         """Merge the statistics cumulated by every rank (paths sharded across
@@ -1789,6 +1896,10 @@ class montecarlo:
         for k in range(4):
             self._moments[k][...] = (buf[at:at + nc]/N).reshape(vshape); at += nc
         self._center = c0.astype(self._center.dtype)
+        if getattr(self, '_center_dev', None) is not None:
+            # later updates cumulate about the common centre
+            self._center_dev.copy_(torch.from_numpy(
+                np.ascontiguousarray(self._center, dtype=float).ravel()))
         if has_hist:
             for j, i in enumerate(np.ndindex(vshape)):
                 nb = len(self._edges[j]) - 1

@@ -99,6 +99,60 @@ def test_config4_jumps_replay_idempotence_chunk():
     assert np.allclose(R.info['jump_rate'], P.info['jump_rate'], rtol=1e-13)
 
 
+@pytest.mark.parametrize('kind', ['merton', 'kou'])
+def test_config4_chunks_against_the_oracle(kind):
+    """Config 4 at its own step count against the ORACLE (not against the
+    kernel's own draws): chunks of 1e5 paths x 1000 steps whose increments are
+    drawn by the oracle's restatement of the reference sources
+    (wiener_source / cpoisson_source, infrastructure.py:1503-1560, 2017-2040),
+    integrated by the kernel in replay mode and by orc.euler_replay('jumpdiff'):
+    paths within 4 ulp (the final exp), jump counts bit-equal.  Chunks are
+    looped until 1e7 paths or a time budget is spent."""
+    import time
+    from oracle import sde_oracle as orc
+    m = sd()
+    chunk, n, budget = 100_000, 1000, 25.
+    grid = np.linspace(0., 1., n + 1)
+    par = dict(mu=.05, sigma=.2)
+    if kind == 'merton':
+        law, cls, lkw = orc.jump_law('norm', a=-.1, b=.15), m.merton_jumpdiff_process, dict(a=-.1, b=.15)
+    else:
+        law, cls = orc.jump_law('double_exp', a=.1, b=.15, pa=.4), m.kou_jumpdiff_process
+        lkw = dict(a=.1, b=.15, pa=.4)
+    rng = np.random.default_rng(404)
+    done, t0, eps = 0, time.perf_counter(), np.finfo(float).eps
+    while done < 10_000_000 and (done == 0 or time.perf_counter() - t0 < budget):
+        dW = np.empty((n, chunk)); dJ = np.empty((n, chunk)); dN = np.empty((n, chunk), dtype=np.int64)
+        for i in range(n):      # sorted-id order of the reference: dj before dw
+            s, ds = grid[i], grid[i + 1] - grid[i]
+            dJ[i], dN[i] = orc.draw_cpoisson(rng, s, ds, (), chunk, 2., law)
+            dW[i] = orc.draw_wiener(rng, s, ds, (), chunk)
+        want, winfo = orc.euler_replay('jumpdiff', par, 1., grid, [0, n], dW, dJ=dJ, dN=dN)
+        P = cls(paths=chunk, steps=grid, x0=1., lam=2., dw=m.replay_source(dW),
+                dj=m.replay_source(dJ, dn=dN), **par, **lkw)
+        got = np.asarray(P((0., 1.)))
+        assert got.shape == want.shape == (2, chunk)
+        assert np.abs(got/want - 1).max() <= 4*eps
+        assert np.array_equal(P.info['jump_count'], winfo['jump_count'])
+        done += chunk
+    assert done >= 2*chunk, 'fewer than two chunks fit the time budget'
+
+
+def test_poisson_counts_at_large_intensity():
+    """lam*|dt| far beyond the inversion range (exp(-lam|dt|) underflows past
+    ~745): counts are drawn as a sum of independent Poisson(lam|dt|/m) variates
+    -- mean and variance of Poisson(L) within 5 standard errors, for L on both
+    sides of the switch at 30 and far beyond it."""
+    m = sd()
+    paths = 400_000
+    for L in (29., 31., 500., 2000.):
+        dn = np.asarray(m.poisson_source(paths=paths, lam=L, seed=int(L))(0., 1.)).astype(float)
+        assert abs(dn.mean() - L) < 5*np.sqrt(L/paths)
+        assert abs(dn.var() - L) < 5*L*np.sqrt(2/paths) + 5*np.sqrt(L/paths)
+        third = ((dn - L)**3).mean()                  # third central moment = L
+        assert abs(third - L) < 6*np.sqrt(15*L**3/paths)
+
+
 def test_config5_milstein_1e8_montecarlo():
     m = sd()
 
