@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SDEB_ABI_VERSION 1
+#define SDEB_ABI_VERSION 2
 
 enum {
     SDEB_OK = 0,
@@ -53,6 +53,7 @@ enum {
 enum { SDEB_NOISE_PHILOX = 0, SDEB_NOISE_REPLAY = 1 };
 enum { SDEB_LAW_NORMAL = 1, SDEB_LAW_UNIFORM = 2, SDEB_LAW_EXP = 3, SDEB_LAW_DOUBLE_EXP = 4 };
 enum { SDEB_PAYOFF_NONE = 0, SDEB_PAYOFF_CALL = 1, SDEB_PAYOFF_PUT = 2 };
+enum { SDEB_F64 = 0, SDEB_F32 = 1, SDEB_F16 = 2 };
 
 /* statistics vector per (row, component): centred power sums S1..S4 of
  * (v - centre), min, max, payoff sum, payoff square sum */
@@ -113,7 +114,8 @@ typedef struct sdeb_problem {
     const double* dW;         /* replay: [n_steps][n_groups*ndw][pitch]         */
     const double* dJ;         /* replay: [n_steps][n_groups*nw][pitch]          */
     const int64_t* dN;        /* replay: same layout, optional                  */
-    double* out;              /* [n_rows][n_groups*nx][pitch], may be NULL      */
+    double* out;              /* [n_rows][n_groups*nx][pitch], may be NULL; elements
+                                 of type out_dtype (float64 unless stated)         */
     double* stats;            /* [n_rows][n_groups*nx][SDEB_NSTAT], may be NULL */
     const double* centre;     /* [n_groups*nx]: shift of the power sums         */
     int64_t payoff_kind;      /* SDEB_PAYOFF_*                                  */
@@ -134,6 +136,10 @@ typedef struct sdeb_problem {
                                  infrastructure.py:2095-2110); 0 = off          */
     int64_t anti_dj_half;     /* K > 0: paths p >= K repeat the jumps of p - K
                                  (even_cpoisson_source, 2133-2150); 0 = off     */
+    int64_t out_dtype;        /* storage type of `out` (paths_generator dtype=,
+                                 integration.py:495-496, 550): SDEB_F64 / SDEB_F32 /
+                                 SDEB_F16.  The state and all arithmetic stay fp64 in
+                                 registers; values are narrowed at the store        */
 } sdeb_problem;
 
 typedef struct sdeb_plan_t {
@@ -152,6 +158,8 @@ typedef struct sdeb_plan_t {
     int64_t smem_bytes;       /* dynamic shared memory per block                */
     int64_t workspace_bytes;  /* scratch needed when stats != NULL              */
     int64_t stats_in_kernel;  /* 0: stats accumulators do not fit in smem       */
+    int64_t kernel;           /* which kernel runs: 0 general, 1 lean (Philox, one
+                                 time-invariant record), 2 stream (full-path output) */
 } sdeb_plan_t;
 
 int sdeb_abi_version(void);

@@ -108,7 +108,7 @@ class run_result:
 def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
         dev=None, replay=None, want_out=True, want_stats=False, centre=None,
         payoff=None, counters=False, dn_sums=False, dump=False, max_blocks=0,
-        anti_dw_half=0, anti_dj_half=0):
+        anti_dw_half=0, anti_dj_half=0, out_dtype=np.dtype(float), trace_kernels=False):
     """Run all segments.  ``records[k]`` is the parameter table of segment k,
     shaped [1 or n_steps, groups, npt]; ``replay`` (optional) is a list of
     dicts with device/host tables 'dW', 'dJ', 'dN' per segment.
@@ -120,7 +120,11 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
     dev = _cuda.device(dev)
     res = run_result()
     gx = spec.groups*spec.nx
-    res.out = _cuda.empty((n_rows, gx, paths), dev) if want_out else None
+    out_dtype = np.dtype(out_dtype)
+    out_code = {np.dtype(np.float64): _lib.F64, np.dtype(np.float32): _lib.F32,
+                np.dtype(np.float16): _lib.F16}[out_dtype]
+    res.out = (_cuda.empty((n_rows, gx, paths), dev, getattr(torch, out_dtype.name))
+               if want_out else None)
     if want_out:
         # rows never reached stay NaN, like the reference's allocation
         # (integration.py:550)
@@ -129,7 +133,7 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
     # (zeroed at the start of every sweep, below)
     res.counter = (_cuda.empty((spec.groups*spec.ncnt, paths), dev, torch.int64)
                    if counters and spec.ncnt else None)
-    res.dn_sum, res.dump = [], []
+    res.dn_sum, res.dump, res.kernels = [], [], []
     stats_total = None
     w0 = np.ascontiguousarray(w0, dtype=float)
     w0_per_path = int(w0.ndim == 3)
@@ -194,7 +198,7 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
                 keep.append(t)
                 setattr(p, name, t.data_ptr())
         if want_out:
-            p.out = res.out.data_ptr()
+            p.out, p.out_dtype = res.out.data_ptr(), out_code
         if res.counter is not None:
             # the reference re-initialises its diagnostics at every sweep
             # (info_begin, integration.py:2421, 2588): keep the last sweep's
@@ -234,6 +238,8 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
             p.workspace, p.workspace_bytes = ws.data_ptr(), plan.workspace_bytes
         with torch.cuda.device(dev):
             _lib.check(_lib.lib.sdeb_integrate(C.byref(p), _cuda.stream_ptr(dev)))
+            if trace_kernels:
+                res.kernels.append(int(_lib.plan(p).kernel))
         if seg_stats is not None:
             stats_total = seg_stats if stats_total is None else _merge_stats(stats_total, seg_stats, seg)
         res.dn_sum.append(dn_d)

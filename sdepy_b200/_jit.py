@@ -323,6 +323,13 @@ JIT_ENTRIES = [
     '        sdeb::integrate_body<sdeb::UserModel, true,\n            sdeb::UserModel::JUMPS ? 1 : SDEB_LEAN_PPT>(a);',
     '}',
     '#endif',
+    '#ifdef SDEB_JIT_STREAM',
+    'extern "C" __global__ void __launch_bounds__(SDEB_THREADS, 2)',
+    'sdeb_jit_entry_stream(const sdeb::KArgs a) {',
+    '    sdeb::stream_body<sdeb::UserModel, (SDEB_JIT_STREAM & 2) ? sdeb::NOISE_REPLAY',
+    '        : sdeb::NOISE_PHILOX, (SDEB_JIT_STREAM & 1) != 0>(a);',
+    '}',
+    '#endif',
     '']
 
 PRESET_FUNCTORS = {

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('SDEB_LIB') or os.path.join(HERE, 'csrc', 'libsdeb.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NSTAT = 8
 (MODEL_LINEAR, MODEL_LINEAR_LOG, MODEL_JUMPDIFF, MODEL_MEANREV,
  MODEL_HULL_WHITE, MODEL_CIR, MODEL_HESTON, MODEL_HESTON_FULL) = range(1, 9)
@@ -17,6 +17,7 @@ MODEL_JIT = 100
 NOISE_PHILOX, NOISE_REPLAY = 0, 1
 LAW_NORMAL, LAW_UNIFORM, LAW_EXP, LAW_DOUBLE_EXP = 1, 2, 3, 4
 PAYOFF_NONE, PAYOFF_CALL, PAYOFF_PUT = 0, 1, 2
+F64, F32, F16 = 0, 1, 2
 
 i64, u64, f64, ptr = C.c_int64, C.c_uint64, C.c_double, C.c_void_p
 
@@ -38,7 +39,7 @@ class Problem(C.Structure):
         ('counter', ptr), ('dn_sum', ptr), ('dW_dump', ptr),
         ('dJ_dump', ptr), ('dN_dump', ptr),
         ('workspace', ptr), ('workspace_bytes', i64), ('max_blocks', i64),
-        ('anti_dw_half', i64), ('anti_dj_half', i64),
+        ('anti_dw_half', i64), ('anti_dj_half', i64), ('out_dtype', i64),
     ]
 
 
@@ -46,7 +47,7 @@ class Plan(C.Structure):
     """struct sdeb_plan_t (include/sdeb.h)."""
     _fields_ = [(k, i64) for k in (
         'nw', 'ndw', 'nx', 'npc', 'npt', 'ncnt', 'jumps', 'blocks',
-        'threads', 'smem_bytes', 'workspace_bytes', 'stats_in_kernel')]
+        'threads', 'smem_bytes', 'workspace_bytes', 'stats_in_kernel', 'kernel')]
 
 
 class SdebError(RuntimeError):

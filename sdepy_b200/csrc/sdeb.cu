@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -60,9 +61,9 @@ struct JitModule {
     std::string source, name;
     cudaLibrary_t lib;                 // stage 0: lean entry + dims
     cudaKernel_t kernel_lean;
-    cudaLibrary_t glib[6];             // general entry, one library per sweep variant
-    cudaKernel_t gkernel[6];
-    bool ghave[6];
+    cudaLibrary_t glib[10];            // general entry, one library per sweep variant
+    cudaKernel_t gkernel[10];          // (0..5), stream entry per variant (6..9)
+    bool ghave[10];
     ModelInfo mi;
 };
 static std::mutex g_jit_mutex;
@@ -104,6 +105,32 @@ static int64_t smem_bytes(const ModelInfo& mi, const sdeb_problem* p, bool stats
     if (p->noise == SDEB_NOISE_REPLAY)       // cp.async ring of the replay table
         bytes += (int64_t)replay_depth(mi.ndw) * mi.ndw * kThreads * 8;
     return bytes;
+}
+
+// The stream kernel serves the full-path output mode of diffusions without jumps:
+// paths stored (float64), no statistics / dumps / antithetic pairing / per-path
+// records, 16-byte aligned rows.  SDEB_NO_STREAM=1 in the environment sends
+// everything to the general kernel (used by the tests to compare the two).
+static bool aligned16(const void* q) { return (((uintptr_t)q) & 15) == 0; }
+static bool stream_shape(const sdeb_problem* p, const ModelInfo& mi) {
+    if (mi.jumps || !p->out || p->stats || p->out_dtype != 0 || p->params_per_path ||
+        p->dW_dump || p->dJ_dump || p->dN_dump || p->anti_dw_half || p->anti_dj_half ||
+        (p->pitch & 1) || !aligned16(p->out) || p->n_steps < 1)
+        return false;
+    if (p->noise == SDEB_NOISE_REPLAY && !aligned16(p->dW)) return false;
+    const char* off = getenv("SDEB_NO_STREAM");
+    return !(off && off[0] == '1');
+}
+static int stream_variant(const sdeb_problem* p) {
+    return 2 * (p->noise == SDEB_NOISE_REPLAY ? 1 : 0) + (p->n_psteps > 1 ? 1 : 0);
+}
+static int64_t stream_smem_bytes(const ModelInfo& mi, const sdeb_problem* p) {
+    int64_t nch = mi.ndw > 1 ? (int64_t)mi.ndw * (mi.ndw + 1) / 2 : 0;
+    int64_t d = 0;
+    if (p->noise != SDEB_NOISE_REPLAY) d += (int64_t)TAB_DOUBLES * SDEB_TAB_COPIES;
+    if (p->n_psteps > 1) d += (int64_t)STEP_CHUNK * (mi.npc + nch);
+    if (p->noise == SDEB_NOISE_REPLAY) d += (int64_t)stream_depth(mi.ndw) * mi.ndw * kThreads * 2;
+    return d * 8;
 }
 
 // the lean kernel serves the hot configuration: Philox draws, one
@@ -157,13 +184,29 @@ static int plan_impl(const sdeb_problem* p, sdeb_plan_t* plan, ModelInfo& mi, bo
     int sm = 148, occ = 2;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess && p->model == SDEB_MODEL_JIT && !use_lean(p, mi) && p->n_paths > 0) {
+    if (e == cudaSuccess && p->model == SDEB_MODEL_JIT && !use_lean(p, mi) && p->n_paths > 0 &&
+        !(stream_shape(p, mi) && stream_smem_bytes(mi, p) <= (227 - 2) * 1024)) {
         // NVRTC models: compile the general kernel of this run's sweep variant
         // (a problem without paths is a query for the model's dimensions)
         int rcj = jit_general_kernel(p->jit_handle, sweep_variant(p), &mi.fn);
         if (rcj) return rcj;
     }
-    const void* fn = use_lean(p, mi) ? mi.fn_lean : mi.fn;
+    // kernel choice: lean (hot Philox configuration) > stream (full-path output) > general
+    bool stream = !use_lean(p, mi) && stream_shape(p, mi) &&
+                  (p->model == SDEB_MODEL_JIT || mi.fn_stream[stream_variant(p)]) &&
+                  stream_smem_bytes(mi, p) <= (227 - 2) * 1024;
+    if (stream && e == cudaSuccess && p->model == SDEB_MODEL_JIT) {
+        int rcj = jit_general_kernel(p->jit_handle, 6 + stream_variant(p),
+                                     &mi.fn_stream[stream_variant(p)]);
+        if (rcj) return rcj;
+    }
+    if (stream) {
+        plan->smem_bytes = stream_smem_bytes(mi, p);
+        tiles = ((p->n_paths + 2 * kThreads - 1) / (2 * kThreads)) * p->n_groups;
+    }
+    plan->kernel = stream ? 2 : (use_lean(p, mi) ? 1 : 0);
+    const void* fn = stream ? mi.fn_stream[stream_variant(p)]
+                            : (use_lean(p, mi) ? mi.fn_lean : mi.fn);
     if (e == cudaSuccess && fn) {
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
         if (plan->smem_bytes > 32 * 1024)   // + ~2 KB of static shared memory
@@ -247,6 +290,9 @@ extern "C" int sdeb_integrate(const sdeb_problem* p, void* stream_) {
     a.n_steps = (int)p->n_steps; a.n_groups = (int)p->n_groups; a.n_rows = (int)p->n_rows;
     a.row0 = (int)p->row0; a.n_psteps = (int)p->n_psteps; a.w0_per_path = (int)p->w0_per_path;
     a.noise = (int)p->noise; a.params_pp = (int)p->params_per_path;
+    if (p->out_dtype < 0 || p->out_dtype > 2)
+        return fail(SDEB_EINVAL, "out_dtype must be 0 (float64), 1 (float32) or 2 (float16)");
+    a.out_dtype = (int)p->out_dtype;
     a.payoff_kind = (int)p->payoff_kind; a.payoff_strike = p->payoff_strike;
     a.payoff_scale = p->payoff_scale;
     a.seed = p->seed;
@@ -258,7 +304,9 @@ extern "C" int sdeb_integrate(const sdeb_problem* p, void* stream_) {
     a.anti_dw_half = p->anti_dw_half; a.anti_dj_half = p->anti_dj_half;
 
     void* args[] = {&a};
-    CUDA_TRY(cudaLaunchKernel(lean ? mi.fn_lean : mi.fn, dim3((unsigned)plan.blocks), dim3(kThreads), args,
+    const void* fn = plan.kernel == 2 ? mi.fn_stream[stream_variant(p)]
+                                      : (lean ? mi.fn_lean : mi.fn);
+    CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)plan.blocks), dim3(kThreads), args,
                               (size_t)plan.smem_bytes, stream));
     if (p->stats) {
         int64_t len = p->n_rows * p->n_groups * mi.nx * NSTAT;
@@ -430,16 +478,26 @@ mc_update_kernel(const double* x, int64_t n, int64_t pitch, const double* centre
                  double* edges, int nbins, int uniform, int copies,
                  double* partials, unsigned long long* counts, unsigned long long* outside) {
     extern __shared__ double sh[];
+    __shared__ int s_exact;       // edges are exactly linspace(lo, hi, nbins + 1)
     const int row = blockIdx.y;
     double* s_edges = sh;                                       // nbins + 1
     unsigned int* s_cnt = (unsigned int*)(sh + nbins + 1);      // copies x (nbins + 1)
     const int cstride = nbins + 1;                              // last slot: outside
     const double* xr = x + (int64_t)row * pitch;
     const double c = centre ? centre[row] : __ddiv_rn(range_stats[row * NSTAT], (double)n);
+    if (threadIdx.x == 0) s_exact = uniform;
+    __syncthreads();
     if (nbins > 0) {
         double* e = edges + (int64_t)row * (nbins + 1);
         if (edges_mode == MC_EDGES_GIVEN) {
-            for (int i = threadIdx.x; i <= nbins; i += blockDim.x) s_edges[i] = e[i];
+            const double glo = e[0], ghi = e[nbins];
+            const double gstep = __ddiv_rn(__dsub_rn(ghi, glo), (double)nbins);
+            for (int i = threadIdx.x; i <= nbins; i += blockDim.x) {
+                const double v = e[i];
+                s_edges[i] = v;
+                const double w = (i == nbins) ? ghi : __dadd_rn(__dmul_rn((double)i, gstep), glo);
+                if (uniform && !(v == w)) s_exact = 0;          // benign race: all write 0
+            }
         } else {
             double lo = range_lo, hi = range_hi;
             if (edges_mode == MC_EDGES_MINMAX) {
@@ -460,33 +518,58 @@ mc_update_kernel(const double* x, int64_t n, int64_t pitch, const double* centre
     __syncthreads();
     const double lo = nbins > 0 ? s_edges[0] : 0.0, hi = nbins > 0 ? s_edges[nbins] : 0.0;
     const double scale = nbins / (hi - lo);
-    unsigned int* my_cnt = s_cnt + ((threadIdx.x >> 5) % copies) * cstride;
+    const double step = __ddiv_rn(__dsub_rn(hi, lo), (double)(nbins > 0 ? nbins : 1));
+    const bool exact = s_exact != 0;
+    // counter copy of this lane: private to its warp, odd and even lanes apart
+    unsigned int* my_cnt = s_cnt + ((((threadIdx.x >> 5) << 1) | (threadIdx.x & 1)) % copies) * cstride;
     double st[NSTAT];
     st[0] = st[1] = st[2] = st[3] = st[6] = st[7] = 0.0;
     st[4] = __longlong_as_double(0x7FF0000000000000LL);
     st[5] = __longlong_as_double(0xFFF0000000000000LL);
-    stream_row(xr, n, [&](double v) {
-        double d = v - c, d2 = d * d;
-        st[0] += d; st[1] += d2; st[2] = fma(d2, d, st[2]); st[3] = fma(d2, d2, st[3]);
-        if (nbins > 0) {
-            int idx;
-            if (!(v >= lo && v <= hi)) {
-                idx = nbins;                                    // outside (or NaN)
-            } else {
-                if (uniform) {
-                    idx = (int)((v - lo) * scale);
-                    idx = idx < 0 ? 0 : (idx > nbins - 1 ? nbins - 1 : idx);
-                } else {
-                    int a = 0, b = nbins;                       // largest idx with edges[idx] <= v
-                    while (b - a > 1) { int m = (a + b) >> 1; if (s_edges[m] <= v) a = m; else b = m; }
-                    idx = a;
-                }
-                while (idx > 0 && v < s_edges[idx]) --idx;
-                while (idx < nbins - 1 && v >= s_edges[idx + 1]) ++idx;
-            }
+    if (nbins > 0 && exact) {
+        // uniform bins: the two edges around the arithmetic guess are RECOMPUTED
+        // (the linspace formula, bit for bit) instead of looked up -- no
+        // data-dependent shared loads; the guess is within one bin of the truth
+        // (numpy.histogram relies on the same), so one branch-free correction
+        // each way lands in numpy's bin
+        stream_row(xr, n, [&](double v) {
+            double d = v - c, d2 = d * d;
+            st[0] += d; st[1] += d2; st[2] = fma(d2, d, st[2]); st[3] = fma(d2, d2, st[3]);
+            int idx = (int)((v - lo) * scale);
+            idx = idx < 0 ? 0 : (idx > nbins - 1 ? nbins - 1 : idx);
+            const double e0 = __dadd_rn(__dmul_rn((double)idx, step), lo);
+            const double e1 = (idx + 1 == nbins) ? hi
+                                                 : __dadd_rn(__dmul_rn((double)(idx + 1), step), lo);
+            const int dec = (v < e0) ? 1 : 0;
+            const int inc = (v >= e1 && idx < nbins - 1) ? 1 : 0;
+            idx += inc - dec;
+            if (!(v >= lo && v <= hi)) idx = nbins;             // outside (or NaN)
             atomicAdd(&my_cnt[idx], 1u);
-        }
-    });
+        });
+    } else {
+        stream_row(xr, n, [&](double v) {
+            double d = v - c, d2 = d * d;
+            st[0] += d; st[1] += d2; st[2] = fma(d2, d, st[2]); st[3] = fma(d2, d2, st[3]);
+            if (nbins > 0) {
+                int idx;
+                if (!(v >= lo && v <= hi)) {
+                    idx = nbins;                                // outside (or NaN)
+                } else {
+                    if (uniform) {
+                        idx = (int)((v - lo) * scale);
+                        idx = idx < 0 ? 0 : (idx > nbins - 1 ? nbins - 1 : idx);
+                    } else {
+                        int a = 0, b = nbins;                   // largest idx with edges[idx] <= v
+                        while (b - a > 1) { int m = (a + b) >> 1; if (s_edges[m] <= v) a = m; else b = m; }
+                        idx = a;
+                    }
+                    while (idx > 0 && v < s_edges[idx]) --idx;
+                    while (idx < nbins - 1 && v >= s_edges[idx + 1]) ++idx;
+                }
+                atomicAdd(&my_cnt[idx], 1u);
+            }
+        });
+    }
     block_fold_stats(st, partials, row);
     if (nbins > 0) {
         __syncthreads();
@@ -521,9 +604,10 @@ extern "C" int sdeb_mc_update(const double* x, int64_t n_rows, int64_t n, int64_
         return fail(SDEB_EINVAL, "sdeb_mc_update: workspace too small");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int blocks = (int)mom_blocks(n_rows, n);
-    // warp-private counter copies: as many as fit ~24 KB (8 CTAs per SM stay resident)
+    // warp-private counter copies (odd / even lanes apart): as many as fit ~24 KB
+    // (8 CTAs per SM stay resident)
     int copies = nbins > 0 ? (int)(24 * 1024 / (4 * (nbins + 1))) : 1;
-    copies = copies < 1 ? 1 : (copies > 8 ? 8 : copies);
+    copies = copies < 1 ? 1 : (copies > 16 ? 16 : copies);
     size_t smem = nbins > 0 ? (size_t)(nbins + 1) * (8 + 4 * copies) : 0;
     if (smem > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute(mc_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1290,7 +1374,7 @@ extern "C" int sdeb_jit_compile(const char* source, const char* model_type, int6
     JitModule jm;
     jm.source = source;
     jm.name = model_type ? model_type : "sdeb_jit.cu";
-    for (int k = 0; k < 6; ++k) jm.ghave[k] = false;
+    for (int k = 0; k < 10; ++k) jm.ghave[k] = false;
     std::vector<char> cubin;
     std::string plog;
     int rc = nvrtc_cubin(jm.source, jm.name, {"-DSDEB_JIT_NO_GENERAL"}, cubin, plog);
@@ -1305,6 +1389,7 @@ extern "C" int sdeb_jit_compile(const char* source, const char* model_type, int6
     CUDA_TRY(cudaMemcpy(dims, dptr, sizeof dims, cudaMemcpyDeviceToHost));
     jm.mi.fn = NULL;
     jm.mi.fn_lean = NULL;
+    for (int k = 0; k < 4; ++k) jm.mi.fn_stream[k] = NULL;
     if (cudaLibraryGetKernel(&jm.kernel_lean, jm.lib, "sdeb_jit_entry_lean") == cudaSuccess &&
         dims[3] + (dims[1] > 1 ? dims[1] * (dims[1] + 1) / 2 : 0) <= MAX_CBANK_PARAMS)
         jm.mi.fn_lean = (const void*)jm.kernel_lean;
@@ -1323,16 +1408,25 @@ static int jit_general_kernel(int64_t handle, int variant, const void** fn) {
     auto it = g_jit.find(handle);
     if (it == g_jit.end()) return fail(SDEB_EINVAL, "unknown JIT handle");
     JitModule& jm = it->second;
-    if (variant < 0 || variant >= 6) return fail(SDEB_EINVAL, "bad sweep variant");
+    if (variant < 0 || variant >= 10) return fail(SDEB_EINVAL, "bad sweep variant");
     if (!jm.ghave[variant]) {
         char def[64];
-        snprintf(def, sizeof def, "-DSDEB_SWEEPS=%d", 1 << variant);
+        std::vector<std::string> defs = {"-DSDEB_JIT_NO_LEAN"};
+        const char* entry = "sdeb_jit_entry";
+        if (variant < 6) {
+            snprintf(def, sizeof def, "-DSDEB_SWEEPS=%d", 1 << variant);
+        } else {        // stream kernel: variant - 6 = 2*replay + time-dependent records
+            defs.push_back("-DSDEB_JIT_NO_GENERAL");
+            snprintf(def, sizeof def, "-DSDEB_JIT_STREAM=%d", variant - 6);
+            entry = "sdeb_jit_entry_stream";
+        }
+        defs.push_back(def);
         std::vector<char> cubin;
         std::string plog;
-        int rc = nvrtc_cubin(jm.source, jm.name, {"-DSDEB_JIT_NO_LEAN", def}, cubin, plog);
+        int rc = nvrtc_cubin(jm.source, jm.name, defs, cubin, plog);
         if (rc) return rc;
         CUDA_TRY(cudaLibraryLoadData(&jm.glib[variant], cubin.data(), NULL, NULL, 0, NULL, NULL, 0));
-        CUDA_TRY(cudaLibraryGetKernel(&jm.gkernel[variant], jm.glib[variant], "sdeb_jit_entry"));
+        CUDA_TRY(cudaLibraryGetKernel(&jm.gkernel[variant], jm.glib[variant], entry));
         jm.ghave[variant] = true;
     }
     *fn = (const void*)jm.gkernel[variant];
@@ -1344,7 +1438,7 @@ extern "C" int sdeb_jit_release(int64_t handle) {
     auto it = g_jit.find(handle);
     if (it == g_jit.end()) return fail(SDEB_EINVAL, "sdeb_jit_release: unknown handle");
     cudaLibraryUnload(it->second.lib);
-    for (int k = 0; k < 6; ++k)
+    for (int k = 0; k < 10; ++k)
         if (it->second.ghave[k]) cudaLibraryUnload(it->second.glib[k]);
     g_jit.erase(it);
     return SDEB_OK;

@@ -100,11 +100,17 @@ class paths_generator:
 
     def __call__(self, timeline):
         """Integrate along ``timeline`` (reference integration.py:476-584)."""
+        # the state and all arithmetic are fp64 in registers; float32 / float16
+        # are STORAGE types of the output (reference integration.py:495-496, 550)
         dtype = float if self.dtype is None else self.dtype
-        if np.dtype(dtype) != np.dtype(float):
+        if np.dtype(dtype) not in _OUT_DTYPES:
             raise NotImplementedError(
-                'the CUDA path integrates in float64 only (dtype={} requested)'
-                .format(dtype))
+                'the CUDA path stores float64, float32 or float16 paths '
+                '(dtype={} requested)'.format(dtype))
+        if np.dtype(dtype) != np.dtype(float) and getattr(self, 'output', 'process') == 'device':
+            raise NotImplementedError(
+                "output='device' containers are float64: use the default "
+                "output='process' with dtype={}".format(np.dtype(dtype)))
         if self.depth < 2:
             raise ValueError('the depth of the integrator algorithm should be '
                              '>= 2, not {}'.format(self.depth))
@@ -189,6 +195,10 @@ class integrator(paths_generator):
 
     def dZ(self, t, dt):
         return {'dt': dt + np.nan}
+
+
+_OUT_DTYPES = {np.dtype(np.float64): _lib.F64, np.dtype(np.float32): _lib.F32,
+               np.dtype(np.float16): _lib.F16}
 
 
 def _wrap(tt, xx):
@@ -533,8 +543,11 @@ class SDE(_jit._traced):
         hook and the log transform (reference begin(), 1154-1164).  Shape
         ``wshape + (1,)`` or, for path-dependent x0, ``wshape + (paths,)``."""
         init_args = self._get_args(self._init_args_keys)
+        dtype = float if self.dtype is None else self.dtype
         for npaths in (1, self.paths):
-            w = np.full(self.wshape + (npaths,), np.nan)
+            # the reference's working array has the requested dtype: x0 is
+            # rounded to it when `init` writes it (integration.py:552-555)
+            w = np.full(self.wshape + (npaths,), np.nan, dtype=dtype)
             try:
                 self._init_paths = npaths
                 self.init(t0, w, **init_args)
@@ -704,7 +717,9 @@ class SDE(_jit._traced):
             dev=self.device, replay=replay, want_out=not want_stats,
             want_stats=want_stats, centre=centre, payoff=self.payoff,
             counters=self.getinfo, dn_sums=self.getinfo and jumps,
-            dump=getattr(self, '_dump_increments', False), **anti)
+            dump=getattr(self, '_dump_increments', False),
+            out_dtype=np.dtype(float if self.dtype is None else self.dtype),
+            trace_kernels=getattr(self, '_trace_kernels', False), **anti)
         if self.getinfo:
             self.info['computed_steps'] = int(sum(s.n_steps for s in segs))
             self.info['stored_steps'] = int(sum((s.store_row >= 0).sum() for s in segs))

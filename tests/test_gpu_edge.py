@@ -332,3 +332,50 @@ def test_cpoisson_with_user_jump_size_objects():
     sd_log = np.sqrt(.04 + 20.*(.1**2 + .15**2))
     assert abs(np.log(x[-1]).mean() - (.05 - .02 + 20.*(-.1))) < 4*sd_log/np.sqrt(4000)
     assert want > 0
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float16])
+def test_float32_float16_storage(dtype):
+    """dtype= of the reference (integration.py:495-496; exercised by its
+    tests/test_processes.py:122, 323 with float16): the output process has the
+    requested dtype, is finite, starts from x0 rounded to it; the arithmetic
+    is fp64 in registers, so the narrow run equals the float64 run of the same
+    seed rounded once at the store (x0 exactly representable)."""
+    m = sd()
+    eps = np.finfo(dtype).eps
+    tl = np.linspace(0., 1., 11)
+    cases = [
+        (m.wiener_process, dict(x0=.5, mu=.1, sigma=.3)),
+        (m.lognorm_process, dict(x0=1., mu=.1, sigma=.3)),      # log(x0) exact in any dtype
+        (m.ornstein_uhlenbeck_process, dict(x0=.25, theta=.2, k=1., sigma=.3)),
+        (m.cox_ingersoll_ross_process, dict(x0=.5, theta=.4, k=1., xi=.2)),
+        (m.hull_white_process, dict(factors=2, x0=((.5,), (.25,)), sigma=.1)),
+        (m.heston_process, dict(x0=1., y0=.25, xi=.3, rho=-.5)),
+        (m.full_heston_process, dict(x0=1., y0=.25, xi=.3, rho=-.5)),
+        (m.merton_jumpdiff_process, dict(x0=1., lam=3., a=-.1, b=.2)),
+    ]
+    for cls, kw in cases:
+        for i0 in (0, 3, -2):
+            ps = cls(paths=33, vshape=(2,), dtype=dtype, seed=3, steps=30, i0=i0, **kw)(tl)
+            ref = cls(paths=33, vshape=(2,), seed=3, steps=30, i0=i0, **kw)(tl)
+            ps, ref = (z if isinstance(z, tuple) else (z,) for z in (ps, ref))
+            for p, r in zip(ps, ref):
+                assert isinstance(p, m.process) and p.dtype == dtype and r.dtype == np.float64
+                assert p.shape == (11, 2, 33) and np.isfinite(p).all()
+                assert (p[i0] == p[i0, ..., 0][..., np.newaxis]).all()
+                np.testing.assert_array_equal(np.asarray(p), np.asarray(r).astype(dtype))
+    # x0 that is not representable: rounded to dtype first, like the reference's
+    # typed working array
+    p = m.lognorm_process(paths=5, dtype=dtype, x0=.1, seed=1)(tl)
+    assert np.allclose(np.asarray(p[0], dtype=float), .1, rtol=4*eps)
+    # traced equations, and statistics (unaffected by the storage type)
+    @m.integrate
+    def f(t, x, a=.3):
+        return {'dt': -a*x, 'dw': .2}
+    p = f(paths=17, dtype=dtype, x0=1., seed=2, steps=20)(tl)
+    r = f(paths=17, x0=1., seed=2, steps=20)(tl)
+    np.testing.assert_array_equal(np.asarray(p), np.asarray(r).astype(dtype))
+    with pytest.raises(NotImplementedError):
+        m.wiener_process(paths=5, dtype=np.int32)(tl)
+    with pytest.raises(NotImplementedError):
+        m.wiener_process(paths=5, dtype=np.float32, output='device')(tl)

@@ -1,0 +1,149 @@
+"""The full-path STREAM kernel (csrc/sde_engine.cuh:stream_body) against the
+general kernel: same seed / same replayed increments -> bit-identical paths and
+diagnostics, whichever kernel the launcher picks (SDEB_NO_STREAM=1 forces the
+general one).  Parity of both with the oracle is tests/test_gpu_parity.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+KERNEL_GENERAL, KERNEL_LEAN, KERNEL_STREAM = 0, 1, 2
+
+
+def sd():
+    import sdepy_b200
+    return sdepy_b200
+
+
+def both(make, timeline, expect_stream=True):
+    """Run make() twice -- stream kernel allowed / forbidden -- and return the
+    two device results after checking which kernels ran."""
+    outs = []
+    for no_stream in ('0', '1'):
+        os.environ['SDEB_NO_STREAM'] = no_stream
+        try:
+            P = make()
+            P._trace_kernels = True
+            x = P(timeline)
+            kern = list(P._last_run.kernels)
+        finally:
+            os.environ.pop('SDEB_NO_STREAM', None)
+        if no_stream == '1':
+            assert KERNEL_STREAM not in kern
+        elif expect_stream:
+            assert kern and all(k == KERNEL_STREAM for k in kern), kern
+        outs.append((x, P))
+    return outs
+
+
+def same(a, b):
+    a, b = (z if isinstance(z, tuple) else (z,) for z in (a, b))
+    assert len(a) == len(b)
+    for u, v in zip(a, b):
+        assert u.x.shape == v.x.shape
+        assert torch.equal(u.x, v.x)
+
+
+def hw_theta(t):
+    return np.array(((.02 + .001*t,), (0.,), (0.,)))
+
+
+def hw_corr(t):
+    c01, c02, c12 = .3*np.cos(t), -.2 + .05*t, .1
+    return np.array(((1, c01, c02), (c01, 1, c12), (c02, c12, 1)))
+
+
+@pytest.mark.parametrize('paths', [2, 510, 5000])
+def test_stream_equals_general_philox(paths):
+    m = sd()
+    tl = np.linspace(0., 2., 71)          # 70 steps: a whole step block + a tail, odd periods
+    cases = [
+        lambda: m.ornstein_uhlenbeck_process(x0=.1, theta=lambda s: .2 + .1*s, k=1., sigma=.3,
+                                             paths=paths, seed=2, output='device'),
+        lambda: m.hull_white_process(factors=3, x0=((.01,), (0.,), (0.,)), theta=hw_theta,
+                                     k=((.1,), (.5,), (1.,)), sigma=((.01,), (.008,), (.005,)),
+                                     corr=hw_corr, paths=paths, seed=3, output='device'),
+        lambda: m.full_heston_process(x0=1., y0=.04, mu=lambda t: .01*t, sigma=1., theta=.04, k=2.,
+                                      xi=.6, rho=-.7, paths=paths, seed=4, output='device'),
+        lambda: m.cox_ingersoll_ross_process(x0=.04, theta=lambda t: .04 + .01*t, k=2., xi=.5,
+                                             paths=paths, vshape=(3,), seed=5, output='device'),
+        # time-invariant records with several lane groups (the lean kernel needs one group)
+        lambda: m.lognorm_process(x0=1., mu=((.01,), (.02,)), sigma=.2, vshape=(2,), paths=paths,
+                                  seed=6, output='device'),
+        lambda: m.wiener_process(x0=0., vshape=(2,), corr=((1, .5), (.5, 1)), paths=paths, seed=7,
+                                 output='device', steps=141),
+    ]
+    for make in cases:
+        (xs, Ps), (xg, Pg) = both(make, tl)
+        same(xs, xg)
+        if 'negative_y_count' in Ps.info:
+            assert torch.equal(Ps.info['negative_y_count'], Pg.info['negative_y_count'])
+
+
+def test_stream_equals_general_replay_and_oracle():
+    from oracle import sde_oracle as orc
+    m = sd()
+    paths, n = 1000, 90
+    grid = np.linspace(0., 1., n + 1)
+    rng = np.random.default_rng(3)
+    dW = rng.standard_normal((n, paths))*np.sqrt(np.diff(grid))[:, None]
+    par = dict(theta=.2, k=1.5, sigma=.3)
+    (xs, _), (xg, _) = both(lambda: m.ornstein_uhlenbeck_process(
+        x0=.1, paths=paths, dw=m.replay_source(dW), output='device', **par), grid)
+    same(xs, xg)
+    want, _ = orc.euler_replay('oruh', par, .1, grid, range(n + 1), dW)
+    assert np.array_equal(xs.x.cpu().numpy(), want)
+    # Heston, both components, every 3rd step stored, time-dependent parameter
+    dW2 = rng.standard_normal((n, 2, paths))*np.sqrt(np.diff(grid))[:, None, None]
+    hp = dict(mu=lambda t: .03 + .01*t, sigma=1., theta=.04, k=2., xi=.6)
+    where = list(range(0, n + 1, 3))
+    (xs, Ps), (xg, Pg) = both(lambda: m.full_heston_process(
+        x0=100., y0=.04, paths=paths, steps=grid, dw=m.replay_source(dW2), output='device',
+        **hp), grid[where])
+    same(xs, xg)
+    (ox, oy), oinfo = orc.euler_replay('heston', hp, 100., grid, where, dW2, y0=.04, full=True)
+    assert np.array_equal(xs[1].x.cpu().numpy(), oy)
+    assert np.abs(xs[0].x.cpu().numpy()/ox - 1).max() <= 4*np.finfo(float).eps
+    assert np.array_equal(Ps.info['negative_y_count'].cpu().numpy(), oinfo['negative_y_count'])
+
+
+def test_stream_backward_sweep_and_per_path_x0():
+    m = sd()
+    paths = 3000
+    tl = np.linspace(0., 1., 31)
+    x0 = np.linspace(.5, 1.5, paths)
+    for i0 in (0, 11, -1):
+        (xs, _), (xg, _) = both(lambda: m.ornstein_uhlenbeck_process(
+            x0=x0, theta=lambda s: .2*s, k=1., sigma=.3, paths=paths, seed=9, i0=i0,
+            steps=91, output='device'), tl)
+        same(xs, xg)
+        assert torch.equal(xs.x[i0].cpu(), torch.from_numpy(x0))
+
+
+def test_stream_traced_sde():
+    m = sd()
+
+    @m.integrate
+    def f(t, x, a=.3, b=.2):
+        return {'dt': -a*x*t, 'dw': b*np.sqrt(1 + x*x)}
+
+    tl = np.linspace(0., 1., 41)
+    for method in ('euler', 'milstein'):
+        (xs, _), (xg, _) = both(lambda: f(paths=4000, x0=1., seed=5, method=method,
+                                          output='device'), tl)
+        same(xs, xg)
+
+
+def test_jump_models_and_odd_pitch_keep_the_general_kernel():
+    m = sd()
+    tl = np.linspace(0., 1., 11)
+    for make in (lambda: m.merton_jumpdiff_process(paths=1000, lam=2., seed=1, output='device'),
+                 lambda: m.ornstein_uhlenbeck_process(paths=1001, theta=lambda t: t, seed=1,
+                                                      output='device')):
+        P = make()
+        P._trace_kernels = True
+        P(tl)
+        assert KERNEL_STREAM not in P._last_run.kernels
