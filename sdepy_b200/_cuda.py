@@ -148,13 +148,13 @@ def _workspace(rows, dev):
     return empty((nbytes // 8,), dev), nbytes
 
 
-def mc_range(x2d, n):
+def mc_range(x2d, n, out=None):
     """Pass 1 of montecarlo's first update (sdeb_mc_range): device tensor
     [rows, NSTAT] holding sum (slot 0), min (4), max (5) of every row.  No
     host synchronisation."""
     dev = x2d.device
     rows, pitch = x2d.shape
-    stats = empty((rows, _lib.NSTAT), dev)
+    stats = empty((rows, _lib.NSTAT), dev) if out is None else out
     ws, ws_bytes = _workspace(rows, dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib.sdeb_mc_range(ptr(x2d), rows, n, pitch, ptr(stats), ptr(ws),
@@ -164,13 +164,13 @@ def mc_range(x2d, n):
 
 def mc_update(x2d, n, *, centre=None, range_stats=None, lo=0., hi=0.,
               edges_mode=_lib.MC_EDGES_GIVEN, edges=None, nbins=0, uniform=True,
-              counts=None, outside=None):
+              counts=None, outside=None, out=None):
     """Fused moments + histogram pass (sdeb_mc_update) over the rows of x2d;
     all arrays are device tensors, the result is the device tensor
     [rows, NSTAT] of centred power sums.  No host synchronisation."""
     dev = x2d.device
     rows, pitch = x2d.shape
-    stats = empty((rows, _lib.NSTAT), dev)
+    stats = empty((rows, _lib.NSTAT), dev) if out is None else out
     ws, ws_bytes = _workspace(rows, dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib.sdeb_mc_update(

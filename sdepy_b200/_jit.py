@@ -39,7 +39,8 @@ UNARY = {'negative': 'neg', 'positive': 'pos', 'absolute': 'abs', 'fabs': 'abs',
          'tanh': 'tanh', 'square': 'square', 'log1p': 'log1p', 'expm1': 'expm1'}
 BINARY = {'add': 'add', 'subtract': 'sub', 'multiply': 'mul',
           'true_divide': 'div', 'divide': 'div', 'maximum': 'max',
-          'minimum': 'min', 'power': 'pow'}
+          'minimum': 'min', 'power': 'pow', 'less': 'lt', 'less_equal': 'le',
+          'greater': 'gt', 'greater_equal': 'ge'}
 
 
 class node:
@@ -81,6 +82,9 @@ class node:
     __mul__, __rmul__ = _bin('mul')
     __truediv__, __rtruediv__ = _bin('div')
     __pow__, __rpow__ = _bin('pow')
+    # comparisons give 0/1-valued nodes (counters of info_next, (y < 0)*1. ...)
+    __lt__, __gt__ = _bin('lt')
+    __le__, __ge__ = _bin('le')
     del _bin
 
     def __neg__(self):
@@ -122,6 +126,8 @@ class tracer:
         return n
 
     def lift(self, z):
+        if isinstance(z, _sym_state):
+            z = z._only()
         return z if isinstance(z, node) else self.leaf(z)
 
     def apply(self, op, *args):
@@ -237,7 +243,8 @@ C_OPS = {
     'log1p': 'log1p({0})', 'expm1': 'expm1({0})', 'pow': 'pow({0}, {1})',
     'max': 'xmax({0}, {1})', 'min': 'xmin({0}, {1})',
     'sign': '(({0} > 0.0) - ({0} < 0.0))', 'ge': '(double)({0} >= {1})',
-    'le': '(double)({0} <= {1})',
+    'le': '(double)({0} <= {1})', 'lt': '(double)({0} < {1})',
+    'gt': '(double)({0} > {1})',
 }
 
 PRELUDE = r'''
@@ -279,6 +286,141 @@ class emitter:
             self.lines.append('double %s = %s;' % (r, C_OPS[n.op].format(*args)))
         self.name[n.id] = r
         return r
+
+
+# --------------------------------------------------------------------------
+# symbolic stand-ins for the hooks that see the whole working array
+# (SDE.let, integration.py:1501-1528; info_next through itervars, 650-659)
+# --------------------------------------------------------------------------
+
+def _axis_index(key, ndim):
+    """The index applied to axis -2 (the last working axis) by a key that is
+    trivial on all other axes: ``[..., k, :]`` / ``[..., a:b, :]``; None for a
+    key that selects everything."""
+    if not isinstance(key, tuple):
+        key = (key,)
+    if all(k is Ellipsis or k == slice(None) for k in key):
+        return None
+    tail = []
+    for k in reversed(key):
+        if k is Ellipsis:
+            break
+        tail.append(k)
+    if len(tail) == 2 and tail[0] == slice(None) and (Ellipsis in key or len(key) == ndim):
+        return tail[1]
+    raise TypeError('only [...], [..., k, :] and [..., a:b, :] index the working '
+                    'state inside a traced let / info_next hook')
+
+
+class _sym_state:
+    """The working array ``wshape + (paths,)`` seen by a traced hook: behaves
+    as variable 0 in arithmetic (single equation) and hands out one node per
+    equation when indexed the way ``SDEs.unpack`` does (integration.py:
+    1735-1757)."""
+
+    __array_priority__ = 1000.
+
+    def __init__(self, owner, variables):
+        self._owner, self._vars = owner, variables
+
+    def _var_of(self, key):
+        o = self._owner
+        idx = _axis_index(key, len(o.wshape) + 1)
+        if idx is None:
+            return None
+        q = len(self._vars)
+        if isinstance(idx, (int, np.integer)) and o.addaxis:
+            return int(idx) % q
+        if isinstance(idx, slice) and not o.addaxis and o._system:
+            d = o.vshape[-1]
+            a = 0 if idx.start is None else idx.start
+            b = q*d if idx.stop is None else idx.stop
+            if idx.step in (None, 1) and b - a == d and a % d == 0:
+                return a//d
+        raise TypeError('unsupported index {!r} on the working state of a traced '
+                        'hook'.format(key))
+
+    def __getitem__(self, key):
+        k = self._var_of(key)
+        return self if k is None else self._vars[k]
+
+    def _only(self):
+        if len(self._vars) != 1:
+            raise TypeError('the working state of a system holds {} variables: '
+                            'select one with self.unpack(x)'.format(len(self._vars)))
+        return self._vars[0]
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kw):
+        args = [a._only() if isinstance(a, _sym_state) else a for a in inputs]
+        return self._only().__array_ufunc__(ufunc, method, *args, **kw)
+
+
+def _delegate(name):
+    def f(self, *a):
+        return getattr(self._only(), name)(*a)
+    return f
+
+
+for _n in ('__add__', '__radd__', '__sub__', '__rsub__', '__mul__', '__rmul__',
+           '__truediv__', '__rtruediv__', '__pow__', '__rpow__', '__neg__', '__abs__',
+           '__lt__', '__le__', '__gt__', '__ge__'):
+    setattr(_sym_state, _n, _delegate(_n))
+
+
+class _sym_out:
+    """Recorder standing for ``out_x`` in ``let(t, out_x, x)``: remembers what
+    is assigned to the whole array or to one equation's slice."""
+
+    def __init__(self, state, var=None, sink=None):
+        self._state, self._var = state, var
+        self.assigned = {} if sink is None else sink
+
+    def __getitem__(self, key):
+        k = self._state._var_of(key)
+        return self if k is None else _sym_out(self._state, k, self.assigned)
+
+    def __setitem__(self, key, value):
+        k = self._state._var_of(key)
+        k = self._var if k is None else k
+        self.assigned['all' if k is None else k] = value
+
+
+class _info_acc:
+    """``self.info[key]`` inside a traced info_next: ``+=`` of a state
+    expression is recorded as a per-path counter."""
+
+    def __init__(self, key, sink):
+        self._key, self._sink = key, sink
+
+    def __iadd__(self, value):
+        self._sink.append((self._key, value))
+        return self
+
+    def __getattr__(self, name):
+        raise NotImplementedError(
+            "only `self.info[key] += f(state)` can be compiled from info_next "
+            '(attribute {!r} used)'.format(name))
+
+
+class _info_recorder(dict):
+    def __init__(self):
+        super().__init__()
+        self.recorded = []
+
+    def __getitem__(self, key):
+        return _info_acc(key, self.recorded)
+
+    def __setitem__(self, key, value):
+        if not isinstance(value, _info_acc):
+            raise NotImplementedError(
+                'info_next may only accumulate into entries created by info_begin')
+
+
+class _sym_itervars(dict):
+    def __missing__(self, key):
+        raise NotImplementedError(
+            "itervars[{!r}] is not available to a compiled info_next: use "
+            "'last_x' (state before the step) or 'new_x' (after it)".format(key))
 
 
 # --------------------------------------------------------------------------
@@ -424,21 +566,86 @@ class _traced:
     def _build(self, t0):
         if getattr(self, '_jit', None) is not None:
             return self._jit
-        from .integration import SDE
-        if type(self).let is not SDE.let:
-            raise NotImplementedError(
-                'a custom let() hook cannot run on the device: traced SDEs '
-                'store the working state (exponentiated when log=True)')
         tr, roots = self._trace(t0)
         milstein = self.method == 'milstein'
         mil = self._milstein_nodes(tr, roots) if milstein else [None]*len(roots)
         sig = self._traced_signature(tr, roots, mil)
         nleaf = len(tr.leaves)
-        src = self._codegen(tr, roots, mil)
+        let = self._trace_let(t0)
+        counters = self._trace_info()
+        src = self._codegen(tr, roots, mil, let, counters)
         handle = _compile(engine_source() + PRELUDE + src, type(self).__name__)
         self._jit = dict(handle=handle, sig=sig, nleaf=nleaf, milstein=milstein,
-                         source=src)
+                         source=src, let=None if let is None else let[1],
+                         counters=[k for k, _, _ in counters])
         return self._jit
+
+    # ---- hooks that are pure functions of the state: traced like `sde` ------
+    def _hook_overridden(self, name):
+        from .integration import SDE, SDEs
+        return getattr(type(self), name) not in (getattr(SDE, name), getattr(SDEs, name))
+
+    def _trace_let(self, t):
+        """A user ``let(t, out_x, x)`` (reference integration.py:1501-1528) run
+        once with a symbolic working state: what it assigns to ``out_x`` -- the
+        whole array or one equation's slice at a time -- becomes the kernel's
+        emit().  Returns None for the default ``out_x[...] = x``, else
+        (tracer, kind, nodes): kind 'single' (one value per element, xshape =
+        vshape) or 'vars' (one per equation, xshape = wshape)."""
+        if not self._hook_overridden('let'):
+            return None
+        tr = tracer()
+        xs = [tr.var(i) for i in range(self._nvars)]
+        state = _sym_state(self, xs)
+        out = _sym_out(state)
+        self.let(np.float64(t), out, state)
+        got = out.assigned
+        if not got:
+            raise NotImplementedError('let() did not assign to out_x')
+        if 'all' in got:
+            v = got['all']
+            if isinstance(v, _sym_state):
+                return None                           # out_x[...] = x
+            return tr, 'single', [tr.lift(v)]
+        if set(got) != set(range(self._nvars)):
+            raise NotImplementedError(
+                'let() must fill every equation\'s slice of out_x (got {})'.format(sorted(got)))
+        return tr, 'vars', [tr.lift(got[k]._only() if isinstance(got[k], _sym_state) else got[k])
+                            for k in range(self._nvars)]
+
+    def _trace_info(self):
+        """A user ``info_next`` (integration.py:1562-1567) of the form
+        ``self.info[key] += f(itervars['last_x'] | itervars['new_x'])``: each
+        accumulation becomes a per-path counter of the kernel.  Returns a list
+        of (key, tracer, node-with-variables) with variables 0..q-1 = last_x,
+        q..2q-1 = new_x; [] when the hook is not overridden."""
+        if not self.getinfo or not self._hook_overridden('info_next'):
+            return []
+        tr = tracer()
+        q = self._nvars
+        last = _sym_state(self, [tr.var(i) for i in range(q)])
+        new = _sym_state(self, [tr.var(q + i) for i in range(q)])
+        real_info, real_iv = self.info, getattr(self, 'itervars', None)
+        rec = _info_recorder()
+        self.info, self.itervars = rec, _sym_itervars(last_x=last, new_x=new)
+        try:
+            self.info_next()
+        finally:
+            self.info = real_info
+            if real_iv is None:
+                del self.itervars
+            else:
+                self.itervars = real_iv
+        out = []
+        for key, v in rec.recorded:
+            if isinstance(v, _sym_state):
+                v = v._only()
+            if not isinstance(v, node):
+                raise NotImplementedError(
+                    'info_next accumulates {!r}, which does not depend on the state: '
+                    'do it in info_end'.format(v))
+            out.append((key, tr, v))
+        return out
 
     def _leaf_values(self, t):
         """Re-trace at time t and return the leaf values (structure checked)."""
@@ -460,6 +667,12 @@ class _traced:
                                     jit_handle=jit['handle']), lead
 
     def _stats_centre(self, w0l):
+        if (getattr(self, '_jit', None) or {}).get('let'):
+            # a user let(): the stored values are not the working state; the
+            # centre is only a shift of the power sums
+            lead, nw = self._lanes()
+            nx = nw//self._nvars if self._jit['let'] == 'single' else nw
+            return np.zeros((w0l.shape[0], nx))
         w = w0l.mean(axis=-1)
         return np.exp(w) if self.log else w
 
@@ -525,7 +738,7 @@ class _traced:
         return block[..., 0] if width == 1 else block
 
     # ---- code generation ----------------------------------------------------
-    def _codegen(self, tr, roots, mil):
+    def _codegen(self, tr, roots, mil, let=None, counters=()):
         """UserModel functor.  A lane owns ``elems`` elements of the last axis,
         each with ``q`` variables (q = 1 for a single equation; elems = 1
         unless the Wiener components are coupled by a correlation matrix);
@@ -566,10 +779,75 @@ class _traced:
                 body += _flush(em, mil[k])
                 body.append('xn{0} = xadd(xn{0}, xmul({1}, xsub(xmul(dw[{2}], dw[{2}]), ds)));'
                             .format(k, em.ref(mil[k]), comp(k)))
+        # info_next counters (integer-valued expressions of the state before /
+        # after the step), one per accumulation and element
+        base = nw if jumps else 0
+        pre, post = [], []
+        for j, (key, ctr, nd) in enumerate(counters):
+            uses_new = _uses_vars(nd, range(q, 2*q))
+            cem = emitter(_literal_slot(ctr),
+                          lambda k: ('x[%s]' % comp(k)) if k < q else 'xn%d' % (k - q))
+            lines = _flush(cem, nd)
+            lines.append('cnt[%d + %d*E + h] += (int)(%s);' % (base, j, cem.ref(nd)))
+            (post if uses_new else pre).append('{ ' + ' '.join(lines) + ' }')
+        body = pre + body + post
         for k in range(q):
             body.append('x[%s] = xn%d;' % (comp(k), k))
         npc = elems*nleaf + (6*nw if jumps else 0)
-        return _model_source(nw, nw, npc, jumps, 6, elems*nleaf, body, self.log, elems)
+        ncnt = base + len(counters)*elems
+        # user let(): emit() body
+        emit, nx = None, nw
+        if let is not None:
+            ltr, kind, nodes = let
+            lem = emitter(_literal_slot(ltr), lambda k: 'x[%s]' % comp(k))
+            emit = []
+            for k, nd in enumerate(nodes):
+                emit += _flush(lem, nd)
+                val = lem.ref(nd)
+                emit.append('v[%s] = %s;' % ('h' if kind == 'single' else comp(k),
+                                             'exp(%s)' % val if self.log else val))
+            nx = elems if kind == 'single' else nw
+        return _model_source(nw, nw, npc, jumps, 6, elems*nleaf, body, self.log, elems,
+                             ncnt=ncnt, nx=nx, emit=emit)
+
+    def _device_info(self, res, tt, segs, replay):
+        """Counters compiled from info_next: added to the entries info_begin
+        created (reference integration.py:1166-1173)."""
+        keys = (getattr(self, '_jit', None) or {}).get('counters') or []
+        if not keys or res.counter is None:
+            return
+        lead, nw = self._lanes()
+        elems = nw//self._nvars
+        base = nw if self._jump_source() is not None else 0
+        c = res.counter.reshape((-1, base + len(keys)*elems, self.paths))
+        for j, key in enumerate(keys):
+            part = c[:, base + j*elems:base + (j + 1)*elems, :]
+            part = part.cpu().numpy().reshape(tuple(lead) + ((elems,) if elems > 1 or
+                                              len(lead) < len(self.vshape) else ()) + (self.paths,))
+            part = part.reshape(self.vshape + (self.paths,))
+            self.info[key] = self.info[key] + part.astype(np.asarray(self.info[key]).dtype)
+
+
+def _uses_vars(nd, which, seen=None):
+    seen = set() if seen is None else seen
+    if nd.id in seen:
+        return False
+    seen.add(nd.id)
+    if nd.op == 'var':
+        return nd.index in which
+    return any(_uses_vars(a, which, seen) for a in nd.args)
+
+
+def _literal_slot(tr):
+    """Leaves of a traced let / info_next are baked into the source: they must
+    be scalars that do not depend on time."""
+    def slot(j):
+        v = np.asarray(tr.leaves[j].value, dtype=float)
+        if v.size != 1:
+            raise NotImplementedError(
+                'array-valued parameters inside let / info_next cannot be compiled')
+        return hexfloat(v.reshape(()))
+    return slot
 
 
 def _flush(em, nd):
@@ -590,10 +868,13 @@ def _join_blocks(a, b):
     return np.concatenate((a, b), axis=1)
 
 
-def _model_source(nw, ndw, npc, jumps, jp_stride, jp_off, body, log, elems):
+def _model_source(nw, ndw, npc, jumps, jp_stride, jp_off, body, log, elems, ncnt=None,
+                  nx=None, emit=None):
+    ncnt = (nw if jumps else 0) if ncnt is None else ncnt
+    nx = nw if nx is None else nx
     lines = ['namespace sdeb {', 'struct UserModel {',
              '    enum { NW = %d, NDW = %d, NX = %d, NPC = %d, NCNT = %d, JUMPS = %d,'
-             % (nw, ndw, nw, npc, nw if jumps else 0, int(jumps)),
+             % (nw, ndw, nx, npc, ncnt, int(jumps)),
              '           JP_STRIDE = %d, JP_OFF = %d };' % (jp_stride, jp_off),
              '    static __device__ __forceinline__ void step(double (&x)[NW], const double* p,',
              '            double ds, const double* dw, const double* dj, int (&cnt)[NCNT + 1]) {']
@@ -603,12 +884,17 @@ def _model_source(nw, ndw, npc, jumps, jp_stride, jp_off, body, log, elems):
     lines += ['            ' + b for b in body]
     lines.append('        }')
     lines += ['    }',
-              '    static __device__ __forceinline__ void emit(const double (&x)[NW], double (&v)[NX]) {',
-              '#pragma unroll',
-              '        for (int c = 0; c < NW; ++c) v[c] = %s;' % ('exp(x[c])' if log else 'x[c]'),
-              '    }', '};', '}',
+              '    static __device__ __forceinline__ void emit(const double (&x)[NW], double (&v)[NX]) {']
+    if emit is None:
+        lines += ['#pragma unroll',
+                  '        for (int c = 0; c < NW; ++c) v[c] = %s;' % ('exp(x[c])' if log else 'x[c]')]
+    else:
+        lines += ['        enum { E = %d };' % elems, '#pragma unroll',
+                  '        for (int h = 0; h < E; ++h) {'] + ['            ' + b for b in emit] + [
+                  '        }']
+    lines += ['    }', '};', '}',
               'extern "C" __constant__ int sdeb_jit_dims[6] = {%d, %d, %d, %d, %d, %d};'
-              % (nw, ndw, nw, npc, nw if jumps else 0, int(jumps)),
+              % (nw, ndw, nx, npc, ncnt, int(jumps)),
               ''] + JIT_ENTRIES
     return '\n'.join(lines)
 
@@ -632,7 +918,8 @@ def evaluate(nd, xs, cache=None):
              'sin': np.sin, 'cos': np.cos, 'tanh': np.tanh, 'log1p': np.log1p,
              'expm1': np.expm1, 'pow': np.power, 'max': np.maximum,
              'min': np.minimum, 'sign': np.sign,
-             'ge': lambda u, v: (u >= v)*1., 'le': lambda u, v: (u <= v)*1.}[nd.op]
+             'ge': lambda u, v: (u >= v)*1., 'le': lambda u, v: (u <= v)*1.,
+             'lt': lambda u, v: (u < v)*1., 'gt': lambda u, v: (u > v)*1.}[nd.op]
         r = f(*a)
     cache[nd.id] = r
     return r

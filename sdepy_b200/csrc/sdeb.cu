@@ -128,7 +128,7 @@ static int64_t stream_smem_bytes(const ModelInfo& mi, const sdeb_problem* p) {
     int64_t nch = mi.ndw > 1 ? (int64_t)mi.ndw * (mi.ndw + 1) / 2 : 0;
     int64_t d = 0;
     if (p->noise != SDEB_NOISE_REPLAY) d += (int64_t)TAB_DOUBLES * SDEB_TAB_COPIES;
-    if (p->n_psteps > 1) d += (int64_t)STEP_CHUNK * (mi.npc + nch);
+    if (p->n_psteps > 1) d += (int64_t)STEP_CHUNK * ((mi.npc + nch + 1) & ~(int64_t)1);
     if (p->noise == SDEB_NOISE_REPLAY) d += (int64_t)stream_depth(mi.ndw) * mi.ndw * kThreads * 2;
     return d * 8;
 }
@@ -527,23 +527,38 @@ mc_update_kernel(const double* x, int64_t n, int64_t pitch, const double* centre
     st[4] = __longlong_as_double(0x7FF0000000000000LL);
     st[5] = __longlong_as_double(0xFFF0000000000000LL);
     if (nbins > 0 && exact) {
-        // uniform bins: the two edges around the arithmetic guess are RECOMPUTED
-        // (the linspace formula, bit for bit) instead of looked up -- no
-        // data-dependent shared loads; the guess is within one bin of the truth
-        // (numpy.histogram relies on the same), so one branch-free correction
-        // each way lands in numpy's bin
+        // Uniform bins.  t = (v - lo) * nbins/(hi - lo) - 1/2, r = rint(t) (two
+        // additions with the 1.5 * 2^52 magic number), f = t - r: f is the
+        // position of v inside bin r, in bin widths from the bin CENTRE.  The
+        // arithmetic t and the exactly-rounded linspace edges e_i disagree with
+        // the ideal affine map by at most `margin` bin widths (a few ulps of
+        // max|lo|,|hi| over the bin width, plus the rounding of t), so an
+        // element farther than that from both edges of bin r is in bin r by
+        // numpy's edge comparisons too: no edge is touched.  The few elements
+        // within `margin` of an edge (and NaN / Inf, whose f is NaN) take the
+        // exact path below.  Out-of-range elements have r outside [0, nbins).
+        const double big = fmax(fabs(lo), fabs(hi));
+        const double margin = (16.0 * big / step + 16.0 * nbins) * 1.1102230246251565e-16;
+        const double f_ok = 0.5 - margin;               // <= 0: everything goes the exact way
+        const double magic = 6755399441055744.0;        // 1.5 * 2^52
         stream_row(xr, n, [&](double v) {
             double d = v - c, d2 = d * d;
             st[0] += d; st[1] += d2; st[2] = fma(d2, d, st[2]); st[3] = fma(d2, d2, st[3]);
-            int idx = (int)((v - lo) * scale);
-            idx = idx < 0 ? 0 : (idx > nbins - 1 ? nbins - 1 : idx);
-            const double e0 = __dadd_rn(__dmul_rn((double)idx, step), lo);
-            const double e1 = (idx + 1 == nbins) ? hi
-                                                 : __dadd_rn(__dmul_rn((double)(idx + 1), step), lo);
-            const int dec = (v < e0) ? 1 : 0;
-            const int inc = (v >= e1 && idx < nbins - 1) ? 1 : 0;
-            idx += inc - dec;
-            if (!(v >= lo && v <= hi)) idx = nbins;             // outside (or NaN)
+            const double t = fma(v - lo, scale, -0.5);
+            const double r = __dadd_rn(__dadd_rn(t, magic), -magic);
+            const double f = t - r;
+            int idx;
+            if (fabs(f) < f_ok) {
+                const unsigned int u = (unsigned int)__double2int_rn(r);   // negative -> huge
+                idx = (int)(u < (unsigned int)nbins ? u : (unsigned int)nbins);
+            } else if (!(v >= lo && v <= hi)) {
+                idx = nbins;                                    // outside (or NaN)
+            } else {
+                idx = (int)((v - lo) * scale);
+                idx = idx < 0 ? 0 : (idx > nbins - 1 ? nbins - 1 : idx);
+                while (idx > 0 && v < s_edges[idx]) --idx;
+                while (idx < nbins - 1 && v >= s_edges[idx + 1]) ++idx;
+            }
             atomicAdd(&my_cnt[idx], 1u);
         });
     } else {

@@ -1586,15 +1586,13 @@ class montecarlo:
             # reference 2928-2930: a floating sample sets the dtype of the results
             dtype = ((sdtype if sdtype.kind == 'f' else float) if self.dtype is None
                      else self.dtype)
-            # pass 1 (sum, min, max): centring constant = first-sample mean
-            # (2934) and the range of numpy.histogram(range=None) (2999-3004)
-            rstats = torch.cat([_cuda.mc_range(rows[r0:r1], m)
-                                for r0, r1 in self._row_chunks(nrow)])
             bins = self._bins
             int_bins = isinstance(bins, (int, np.integer)) and not isinstance(bins, bool)
             if np.dtype(dtype) == np.dtype(float) and (bins is None or int_bins):
-                # pass 2 builds centre and edges on the device from pass 1's
-                # result: no host round trip between the two passes
+                # Two launches, ONE device-to-host copy: pass 1 (sum, min, max:
+                # the centring constant = first-sample mean, 2934, and the range
+                # of numpy.histogram(range=None), 2999-3004) feeds pass 2 on the
+                # device, which builds centre and edges itself.
                 nb = 0 if bins is None else int(bins)
                 if bins is not None and nb < 1:
                     raise ValueError('`bins` must be positive, when an integer')
@@ -1607,9 +1605,11 @@ class montecarlo:
                         raise ValueError('supplied range of [{}, {}] is not finite'.format(a, b))
                     mode = _lib.MC_EDGES_RANGE
                 groups = self._alloc_groups([nb]*nrow, [True]*nrow, rows.device)
-                st = self._launch(groups, rows, m, None, rstats, mode, a, b)
-                rs = rstats.cpu().numpy()
-                st = st.cpu().numpy()
+                for g in groups:
+                    _cuda.mc_range(rows[g['r0']:g['r1']], m, out=g['range'])
+                host = self._launch(groups, rows, m, None, True, mode, a, b)
+                rs = np.concatenate([h['range'] for h in host])
+                st = np.concatenate([h['stats'] for h in host])
                 if nb and mode == _lib.MC_EDGES_MINMAX:
                     for i in range(nrow):
                         # a NaN anywhere in the sample makes numpy's range NaN
@@ -1620,35 +1620,43 @@ class montecarlo:
                                              .format(lo_i, hi_i))
                 center = (rs[:, 0]/m).reshape(vshape)
                 self._groups = groups
-                self._center_dev = _cuda.to_device(center.ravel(), rows.device)
+                at = 0
+                for g in groups:        # later updates cumulate about the same centre
+                    k = g['r1'] - g['r0']
+                    g['centre'].copy_(torch.from_numpy(center.reshape(-1)[at:at + k]),
+                                      non_blocking=True)
+                    at += k
                 if nb:
                     self._edges, self._uniform = [], [True]*nrow
-                    for g in groups:
-                        e = g['edges'].cpu().numpy()
-                        self._edges += [e[i] for i in range(e.shape[0])]
+                    for h in host:
+                        self._edges += [h['edges'][i] for i in range(h['edges'].shape[0])]
                     self._bins = np.empty(vshape, dtype=object)
                     for j, i in enumerate(np.ndindex(vshape)):
                         self._bins[i] = self._edges[j]
             else:
+                rstats = torch.cat([_cuda.mc_range(rows[r0:r1], m)
+                                    for r0, r1 in self._row_chunks(nrow)])
                 rs = rstats.cpu().numpy()
                 center = (rs[:, 0]/m).reshape(vshape).astype(dtype)
                 lo, hi = rs[:, 4], rs[:, 5]
-                self._center_dev = _cuda.to_device(
-                    np.asarray(center, dtype=float).ravel(), rows.device)
+                cflat = np.asarray(center, dtype=float).ravel()
                 centred = None
                 if isinstance(bins, str):
                     # named estimators need the centred moments of the sample
-                    g0 = self._alloc_groups([0]*nrow, [True]*nrow, rows.device)
-                    centred = self._launch(g0, rows, m, self._center_dev).cpu().numpy()
+                    g0 = self._alloc_groups([0]*nrow, [True]*nrow, rows.device, centre=cflat)
+                    centred = np.concatenate(
+                        [h['stats'] for h in self._launch(g0, rows, m, 'own')])
                 if bins is not None:
                     self._setup_bins(vshape, lo, hi, rows=rows, m=m, centred=centred,
                                      integer=np.issubdtype(
                                          getattr(sample, 'dtype', np.dtype(float))
                                          if isinstance(sample, np.ndarray) else float,
-                                         np.integer))
+                                         np.integer), centre=cflat)
                 else:
-                    self._groups = self._alloc_groups([0]*nrow, [True]*nrow, rows.device)
-                st = self._launch(self._groups, rows, m, self._center_dev).cpu().numpy()
+                    self._groups = self._alloc_groups([0]*nrow, [True]*nrow, rows.device,
+                                                      centre=cflat)
+                host = self._launch(self._groups, rows, m, 'own')
+                st = np.concatenate([h['stats'] for h in host])
             self._center = center
             self._moments = tuple(np.zeros(vshape, dtype=dtype) for _ in range(4))
             self._mean = np.zeros(vshape, dtype=dtype)
@@ -1656,23 +1664,27 @@ class montecarlo:
             if vshape != self.vshape:
                 raise ValueError('sample of shape {} incompatible with the shape {} of '
                                  'the cumulated data'.format(vshape, self.vshape))
-            st = self._launch(self._groups, rows, m, self._center_dev).cpu().numpy()
+            host = self._launch(self._groups, rows, m, 'own')
+            st = np.concatenate([h['stats'] for h in host])
         for k in range(4):
             mk = (st[:, k]/m).reshape(vshape)
             self._moments[k][...] = (n*self._moments[k] + m*mk)/(n + m)
         smean = self._center + (st[:, 0]/m).reshape(vshape)
         self._mean[...] = (n*self._mean + m*smean)/(n + m)
         if self._bins is not None:
-            self._read_histogram(m)
+            self._read_histogram(m, host)
         self._paths[0] += m
 
     @staticmethod
     def _row_chunks(nrow, width=32768):
         return [(r0, min(nrow, r0 + width)) for r0 in range(0, nrow, width)]
 
-    def _alloc_groups(self, nbins, uniform, dev, edges=None):
+    def _alloc_groups(self, nbins, uniform, dev, edges=None, centre=None):
         """Partition the rows into runs sharing (nbins, uniform) -- one fused
-        launch each -- and allocate their device edges / int64 counters."""
+        launch each.  Everything a launch reads or writes besides the sample
+        lives in ONE device buffer per group (range statistics, power sums,
+        centre, edges, int64 counters), so that a single device-to-host copy
+        brings an update's results back."""
         groups, r0, nrow = [], 0, len(nbins)
         while r0 < nrow:
             r1 = r0 + 1
@@ -1680,13 +1692,25 @@ class montecarlo:
                    and uniform[r1] == uniform[r0]):
                 r1 += 1
             nb, k = int(nbins[r0]), r1 - r0
-            g = dict(r0=r0, r1=r1, nbins=nb, uniform=bool(uniform[r0]), edges=None,
-                     counts=None, outside=None)
+            ns = _lib.NSTAT
+            sizes = dict(range=k*ns, stats=k*ns, centre=k, edges=k*(nb + 1) if nb else 0,
+                         counts=k*nb, outside=k if nb else 0)
+            buf = _cuda.zeros((sum(sizes.values()),), dev)
+            g = dict(r0=r0, r1=r1, nbins=nb, uniform=bool(uniform[r0]), buf=buf, sizes=sizes)
+            at = 0
+            for name, size in sizes.items():
+                v = buf[at:at + size]
+                at += size
+                if name in ('counts', 'outside'):
+                    v = v.view(torch.int64)
+                g[name] = v if size else None
+            g['range'], g['stats'] = g['range'].view(k, ns), g['stats'].view(k, ns)
             if nb:
-                g['edges'] = (_cuda.empty((k, nb + 1), dev) if edges is None else
-                              _cuda.to_device(np.stack(edges[r0:r1]), dev, dtype=float))
-                g['counts'] = _cuda.zeros((k, nb), dev, torch.int64)
-                g['outside'] = _cuda.zeros((k,), dev, torch.int64)
+                g['edges'], g['counts'] = g['edges'].view(k, nb + 1), g['counts'].view(k, nb)
+                if edges is not None:
+                    g['edges'].copy_(torch.from_numpy(np.stack(edges[r0:r1]).astype(float)))
+            if centre is not None:
+                g['centre'].copy_(torch.from_numpy(np.ascontiguousarray(centre[r0:r1], dtype=float)))
             groups.append(g)
             r0 = r1
         # per-row views (montecarlo.allreduce writes the merged counts back)
@@ -1697,19 +1721,33 @@ class montecarlo:
         return groups
 
     @staticmethod
-    def _launch(groups, rows, m, centre_dev, rstats=None, mode=_lib.MC_EDGES_GIVEN,
+    def _launch(groups, rows, m, centre, from_range=False, mode=_lib.MC_EDGES_GIVEN,
                 lo=0., hi=0.):
-        """One fused moments + histogram launch per group; device [rows, NSTAT]."""
-        out = []
+        """One fused moments + histogram launch per group, then ONE device-to-
+        host copy of the group's buffer.  Returns per group a dict of host
+        arrays (range, stats, centre, edges, counts, outside)."""
         for g in groups:
             r0, r1 = g['r0'], g['r1']
-            out.append(_cuda.mc_update(
-                rows[r0:r1], m,
-                centre=None if centre_dev is None else centre_dev[r0:r1],
-                range_stats=None if rstats is None else rstats[r0:r1],
+            _cuda.mc_update(
+                rows[r0:r1], m, centre=g['centre'] if centre == 'own' else None,
+                range_stats=g['range'] if from_range else None,
                 lo=lo, hi=hi, edges_mode=mode, edges=g['edges'], nbins=g['nbins'],
-                uniform=g['uniform'], counts=g['counts'], outside=g['outside']))
-        return out[0] if len(out) == 1 else torch.cat(out)
+                uniform=g['uniform'], counts=g['counts'], outside=g['outside'],
+                out=g['stats'])
+        host = []
+        for g in groups:
+            flat = g['buf'].cpu().numpy()
+            k, nb, ns = g['r1'] - g['r0'], g['nbins'], _lib.NSTAT
+            h, at = {}, 0
+            for name, size in g['sizes'].items():
+                v = flat[at:at + size]
+                at += size
+                h[name] = v.view(np.int64) if name in ('counts', 'outside') else v
+            h['range'], h['stats'] = h['range'].reshape(k, ns), h['stats'].reshape(k, ns)
+            if nb:
+                h['edges'], h['counts'] = h['edges'].reshape(k, nb + 1), h['counts'].reshape(k, nb)
+            host.append(h)
+        return host
 
     @staticmethod
     def _bin_width(name, row, n, a, b, mom, integer):
@@ -1765,7 +1803,8 @@ class montecarlo:
             w = 1
         return w
 
-    def _setup_bins(self, vshape, lo, hi, rows=None, m=0, centred=None, integer=False):
+    def _setup_bins(self, vshape, lo, hi, rows=None, m=0, centred=None, integer=False,
+                    centre=None):
         bins = self._bins
         nrow = int(np.prod(vshape, dtype=int))
         dev = rows.device if rows is not None else _cuda.device(self._device)
@@ -1822,22 +1861,22 @@ class montecarlo:
                 self._edges.append(e)
                 self._uniform.append(False)
         self._groups = self._alloc_groups([len(e) - 1 for e in self._edges], self._uniform,
-                                          dev, edges=self._edges)
+                                          dev, edges=self._edges, centre=centre)
         self._bins = np.empty(vshape, dtype=object)
         for j, i in enumerate(np.ndindex(vshape)):
             self._bins[i] = self._edges[j]
 
-    def _read_histogram(self, m):
-        """Host copies of the cumulated counts (one D2H per launch group)."""
+    def _read_histogram(self, m, host):
+        """Cumulated counts of this update's device-to-host copy."""
         vshape = self.vshape
         self._counts = np.empty(vshape, dtype=object)
         self._paths_outside = np.zeros(vshape, dtype=self.ctype)
         index = list(np.ndindex(vshape))
-        for g in self._groups:
-            c, o = g['counts'].cpu().numpy(), g['outside'].cpu().numpy()
+        for g, h in zip(self._groups, host):
+            c, o = h['counts'], h['outside']
             for k in range(g['r1'] - g['r0']):
                 i = index[g['r0'] + k]
-                self._counts[i] = c[k].astype(self.ctype, copy=False)
+                self._counts[i] = c[k].astype(self.ctype)
                 self._paths_outside[i] = int(o[k])
                 if self._counts[i].sum() + self._paths_outside[i] != self.paths + m:
                     raise RuntimeError(
@@ -1896,10 +1935,10 @@ class montecarlo:
         for k in range(4):
             self._moments[k][...] = (buf[at:at + nc]/N).reshape(vshape); at += nc
         self._center = c0.astype(self._center.dtype)
-        if getattr(self, '_center_dev', None) is not None:
+        cflat = np.ascontiguousarray(self._center, dtype=float).ravel()
+        for g in getattr(self, '_groups', ()):
             # later updates cumulate about the common centre
-            self._center_dev.copy_(torch.from_numpy(
-                np.ascontiguousarray(self._center, dtype=float).ravel()))
+            g['centre'].copy_(torch.from_numpy(cflat[g['r0']:g['r1']]))
         if has_hist:
             for j, i in enumerate(np.ndindex(vshape)):
                 nb = len(self._edges[j]) - 1

@@ -348,6 +348,10 @@ class SDE(_jit._traced):
     q = None
     addaxis = None
     _preset = None          # name of the hand-written kernel functor, if any
+    # traced equations: let() and info_next() are compiled into the kernel
+    # (_jit._trace_let / _trace_info), info_begin / info_end run on the host
+    # before / after the launch; the other per-step hooks cannot take effect
+    _stepping_hooks = ('begin', 'next', 'store', 'end', 'A', 'dZ', 'info_store')
 
     # ---- argument bookkeeping (reference 970-1076) -----------------------
     def _check_source_id(self, id):
@@ -678,6 +682,14 @@ class SDE(_jit._traced):
                 'integration method {!r} has no device implementation '
                 '(available: {})'.format(self.method, self._device_schemes))
         segs = _engine.segments_of(tt, grid, self.i0)
+        # user info hooks of a traced equation: info_begin / info_end run here,
+        # on the host, around the launch (reference integration.py:1166, 1189)
+        user_info = self.getinfo and self._preset is None and not isinstance(
+            self, _preset_SDE) and any(self._hook_overridden(h) for h in
+                                       ('info_begin', 'info_next', 'info_end'))
+        if user_info:
+            self.itervars = dict(tt=tt, steps_tt=grid, i0=self.i0)
+            self.info_begin()
         spec, lead = self._spec()
         replay = self._noise_plan(segs)
         # the lowered tables depend only on the grid and on the parameters:
@@ -724,6 +736,9 @@ class SDE(_jit._traced):
             self.info['computed_steps'] = int(sum(s.n_steps for s in segs))
             self.info['stored_steps'] = int(sum((s.store_row >= 0).sum() for s in segs))
             self._device_info(res, tt, segs, replay)
+            if user_info:
+                self.info_end()
+                del self.itervars
         self._last_run = res
         xshape = self.xshape
         if want_stats:
@@ -761,8 +776,7 @@ class SDE(_jit._traced):
         return (tt.tobytes(), grid.tobytes(), self.i0, replay, self.method,
                 tuple((k, ident(v)) for k, v in sorted(self._args.items())), tuple(srcs))
 
-    def _device_info(self, res, tt, segs, replay):
-        pass
+    # (_device_info: counters compiled from info_next, _jit._traced)
 
     def _counter(self, res, shape):
         c = res.counter.reshape(shape + (self.paths,))
@@ -872,7 +886,8 @@ class SDEs(SDE):
         return a.swapaxes(ax, ax + 1)
 
     def _from_lanes(self, a, tail):
-        if self.addaxis or self._stacked_coupled():
+        if (self.addaxis or self._stacked_coupled()
+                or (getattr(self, '_jit', None) or {}).get('let') == 'single'):
             return super()._from_lanes(a, tail)
         v, q = self.vshape, self.q
         a = a.reshape(a.shape[:1] + v + (q,) + tail)
@@ -937,6 +952,11 @@ class _preset_SDE(SDE):
     _model = None           # SDEB_MODEL_*
     _coupled = False        # lanes own the last working axis regardless of corr
     _device_schemes = ('euler',)
+    # hand-written functors: no user hook can be compiled in
+    _stepping_hooks = paths_generator._stepping_hooks + ('let',)
+
+    def _device_info(self, res, tt, segs, replay):
+        pass
 
     def _lanes(self):
         if self._coupled:

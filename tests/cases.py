@@ -76,3 +76,65 @@ REPLAY = {
     'replay_oruh_ragged': ('ornstein_uhlenbeck',
                            dict(theta=.5, k=2., sigma=.4), dict(x0=1.)),
 }
+
+
+# --------------------------------------------------------------------------
+# user plug points let / info_begin / info_next / info_end on user-defined
+# classes (reference integration.py:1154-1197, 1501-1581).  `m` is the package
+# providing SDE / SDEs / integrator / process: the reference when the golden
+# fixture is generated (tests/golden/make_user_hooks.py), sdepy_b200 in the tests.
+# --------------------------------------------------------------------------
+
+def user_hooks_single(m):
+    class A_SDE(m.SDE):
+        def sde(self, t, x, k=1., s=.4):
+            return {'dt': -k*x, 'dw': s}
+
+        def let(self, t, out_x, x):
+            out_x[...] = x*x + 1.
+
+        def info_begin(self):
+            self.info['neg'] = np.zeros(self.vshape + (self.paths,), dtype=int)
+            self.info['big'] = np.zeros(self.vshape + (self.paths,), dtype=int)
+
+        def info_next(self):
+            iv = self.itervars
+            self.info['neg'] += (iv['last_x'] < 0)
+            self.info['big'] += (iv['new_x'] > .25)
+
+        def info_end(self):
+            self.info['total_neg'] = int(self.info['neg'].sum())
+
+    class A(A_SDE, m.integrator):
+        pass
+    return A
+
+
+def user_hooks_system(m):
+    class B_SDE(m.SDEs):
+        q = 2
+
+        def sde(self, t, x, y, a=.5):
+            return ({'dt': -a*x, 'dw': y}, {'dt': a*(1 - y), 'dw': .2*y})
+
+        def shapes(self, vshape):
+            vshape, xshape, wshape = super().shapes(vshape)
+            return vshape, vshape, wshape
+
+        def let(self, t, out_x, X):
+            x, y = self.unpack(X)
+            out_x[...] = x*y
+
+        def result(self, tt, xx):
+            return m.process(tt, x=xx)
+
+        def info_begin(self):
+            self.info['ylow'] = np.zeros(self.vshape + (self.paths,), dtype=int)
+
+        def info_next(self):
+            x, y = self.unpack(self.itervars['last_x'])
+            self.info['ylow'] += (y < .9)
+
+    class B(B_SDE, m.integrator):
+        pass
+    return B

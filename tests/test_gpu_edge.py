@@ -350,8 +350,8 @@ def test_float32_float16_storage(dtype):
         (m.ornstein_uhlenbeck_process, dict(x0=.25, theta=.2, k=1., sigma=.3)),
         (m.cox_ingersoll_ross_process, dict(x0=.5, theta=.4, k=1., xi=.2)),
         (m.hull_white_process, dict(factors=2, x0=((.5,), (.25,)), sigma=.1)),
-        (m.heston_process, dict(x0=1., y0=.25, xi=.3, rho=-.5)),
-        (m.full_heston_process, dict(x0=1., y0=.25, xi=.3, rho=-.5)),
+        (m.heston_process, dict(x0=1., y0=.25, xi=.3, rho=(-.5, -.3))),
+        (m.full_heston_process, dict(x0=1., y0=.25, xi=.3, rho=(-.5, -.3))),
         (m.merton_jumpdiff_process, dict(x0=1., lam=3., a=-.1, b=.2)),
     ]
     for cls, kw in cases:

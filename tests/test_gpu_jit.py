@@ -395,3 +395,42 @@ def test_explicit_time_in_traced_sde_replay_bit_exact():
     frozen = orc.generic_replay(lambda t, x, a: {'dt': a*(0. - x), 'dw': 1.}, dict(a=2.),
                                 .5, grid, where, dW)
     assert np.abs(x[-1] - frozen[-1]).max() > .1
+
+
+def test_user_let_and_info_hooks_bit_exact_vs_reference():
+    """User classes with `let`, `info_begin`, `info_next`, `info_end` overrides
+    (tests/cases.py:user_hooks_*): the reference ran them on its own recorded
+    increments (tests/golden/make_user_hooks.py); the kernel replays the same
+    increments with the hooks compiled in -- stored values and counters bit for
+    bit (the let bodies only multiply and add)."""
+    from tests.cases import golden, user_hooks_single, user_hooks_system
+    import sdepy_b200 as m
+    g = golden('replay_user_hooks')
+    A = user_hooks_single(m)
+    kw = dict(paths=37, vshape=(2,), steps=23, x0=.3, k=g['a_k'])
+    P = A(dw=m.replay_source(g['a_dW']), **kw)
+    x = P(g['a_tt'])
+    assert isinstance(x, m.process) and x.shape == g['a_out'].shape
+    assert np.array_equal(np.asarray(x), g['a_out'])
+    assert np.array_equal(P.info['neg'], g['a_neg'])
+    assert np.array_equal(P.info['big'], g['a_big'])
+    assert P.info['total_neg'] == int(g['a_total_neg'])
+    # Philox mode, device and stats outputs go through the same compiled hooks
+    Q = A(seed=3, output='device', **kw)
+    xd = Q(g['a_tt'])
+    S = A(seed=3, output='stats', **kw)
+    st = S(g['a_tt'])
+    assert np.allclose(np.asarray(st.pmean())[..., 0], np.asarray(xd.pmean())[..., 0], rtol=1e-12)
+    assert (xd.x >= 1.).all()                       # x*x + 1
+    assert np.array_equal(S.info['neg'], Q.info['neg']) and Q.info['neg'].sum() > 0
+
+    B = user_hooks_system(m)
+    kw = dict(paths=29, vshape=(3,), steps=19, x0=(1., .8))
+    P = B(dw=m.replay_source(g['b_dW']), **kw)
+    x = P(g['b_tt'])
+    assert isinstance(x, m.process) and x.shape == g['b_out'].shape == (5, 3, 29)
+    assert np.array_equal(np.asarray(x), g['b_out'])
+    assert np.array_equal(P.info['ylow'], g['b_ylow'])
+    # getinfo=False: no counters, same paths
+    P = B(dw=m.replay_source(g['b_dW']), getinfo=False, **kw)
+    assert np.array_equal(np.asarray(P(g['b_tt'])), g['b_out']) and 'ylow' not in P.info

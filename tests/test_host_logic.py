@@ -348,8 +348,9 @@ def test_kfunc_parameter_management():
 
 def test_python_stepping_hooks_fail_loudly():
     """A user-written ``next`` (the reference's plug point for Python
-    integration schemes, quickguide.rst:474-498) or per-step ``info_next``
-    cannot run inside the kernel: NotImplementedError before any device work,
+    integration schemes, quickguide.rst:474-498) or a per-step ``info_store``
+    (``let`` / ``info_next`` of traced equations ARE compiled, see
+    test_user_let_and_info_next_are_traced) cannot run inside the kernel: NotImplementedError before any device work,
     never a silent Euler run."""
     import sdepy_b200 as m
 
@@ -365,10 +366,16 @@ def test_python_stepping_hooks_fail_loudly():
         pass
 
     class chatty(my_SDE, m.integrator):
+        def info_store(self):
+            pass
+
+    class tuned(m.lognorm_process):       # hand-written functor: nothing can be compiled in
         def info_next(self):
             pass
 
-    for cls, hook in ((rk, 'next'), (chatty, 'info_next')):
+    with pytest.raises(NotImplementedError, match='info_next'):
+        tuned(paths=10, steps=5)((0., 1.))
+    for cls, hook in ((rk, 'next'), (chatty, 'info_store')):
         with pytest.raises(NotImplementedError, match=hook):
             cls(paths=10, x0=1., steps=5)((0., 1.))
 
@@ -437,3 +444,47 @@ def test_sde_return_value_errors_follow_reference():
     for bad in (np.zeros((2, 2)), (0., 1., .5)):
         with pytest.raises(ValueError):
             m.lognorm_process(paths=3)(bad)
+
+
+def test_user_let_and_info_next_are_traced():
+    """`let` and `info_next` are pure functions of the state: they are traced
+    like `sde` (reference plug points integration.py:1501-1528, 1562-1567) and
+    become the kernel's emit() / per-path counters.  CPU check of the tracer and
+    of the generated functor source (the GPU run against the reference-made
+    fixture is tests/test_gpu_jit.py)."""
+    import sdepy_b200 as m
+    from sdepy_b200 import _jit
+    from tests.cases import user_hooks_single, user_hooks_system
+    A = user_hooks_single(m)(paths=5, vshape=(2,), steps=7, x0=.3)
+    tr, kind, nodes = A._trace_let(0.)
+    assert kind == 'vars' or kind == 'single'
+    x = np.array([-.5, 2.])
+    assert np.array_equal(_jit.evaluate(nodes[0], [x]), x*x + 1.)
+    A.info_begin()
+    cnts = A._trace_info()
+    assert [k for k, _, _ in cnts] == ['neg', 'big']
+    assert np.array_equal(_jit.evaluate(cnts[0][2], [x, x]), (x < 0)*1.)
+    assert np.array_equal(_jit.evaluate(cnts[1][2], [x*0, x]), (x > .25)*1.)
+    assert isinstance(A.info['neg'], np.ndarray)          # the real dict is back
+    t, roots = A._trace(0.)
+    src = A._codegen(t, roots, [None], (tr, kind, nodes), cnts)
+    assert 'NCNT = 2' in src and 'cnt[0 + 0*E + h] += (int)' in src
+    assert 'cnt[0 + 1*E + h] += (int)' in src and 'xn0' in src.split('cnt[0 + 1*E')[1][:80] + src
+    B = user_hooks_system(m)(paths=5, vshape=(3,), steps=7, x0=(1., .8))
+    assert B.xshape == (3,) and B.wshape == (6,)
+    tr, kind, nodes = B._trace_let(0.)
+    assert kind == 'single' and len(nodes) == 1
+    assert np.array_equal(_jit.evaluate(nodes[0], [np.array(2.), np.array(.25)]), .5)
+    t, roots = B._trace(0.)
+    src = B._codegen(t, roots, [None, None], (tr, kind, nodes), B._trace_info())
+    assert 'NX = 1' in src and 'v[h] = ' in src
+
+    class bad(m.SDE, m.integrator):
+        def sde(self, t, x):
+            return {'dt': -x, 'dw': 1.}
+
+        def info_next(self):
+            self.info['n'] += self.itervars['last_dZ']['dw']
+
+    with pytest.raises(NotImplementedError, match='last_dZ'):
+        bad(paths=3)._trace_info()

@@ -41,8 +41,11 @@ def main():
     q = np.linspace(-3., 3., 16)
     rec('device_process.cdf, 16 thresholds', timed(lambda: dp.cdf(q)))
     rec('device_process.chf, 16 frequencies', timed(lambda: dp.chf(q)))
-    rec('montecarlo(x, bins=100): mean pass + min/max + moments + histogram',
-        timed(lambda: sd.montecarlo(x[0], bins=100)), 4)
+    rec('montecarlo(x, bins=100), whole call: range pass + fused moments/histogram pass + D2H',
+        timed(lambda: sd.montecarlo(x[0], bins=100)), 2)
+    mc = sd.montecarlo(x[0], bins=100)
+    rec('montecarlo.update(x) on a cumulating object: one fused pass + D2H',
+        timed(lambda: mc.update(x[0])), 1)
     print(json.dumps(res, indent=1))
 
 
