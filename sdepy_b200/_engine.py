@@ -289,7 +289,7 @@ class resident_stats_run:
             stats=_cuda.empty((tt.size, gx, _lib.NSTAT), dev))
         p = self.p = _lib.Problem()
         p.abi_version = _lib.ABI_VERSION
-        p.model, p.ncomp = spec.model, spec.ncomp
+        p.model, p.ncomp, p.jit_handle = spec.model, spec.ncomp, spec.jit_handle
         p.noise = _lib.NOISE_PHILOX
         p.n_paths, p.path_offset, p.pitch = sde.paths, sde.path_offset, sde.paths
         p.n_steps, p.n_groups, p.n_rows = seg.n_steps, spec.groups, tt.size

@@ -486,11 +486,12 @@ PRESET_FUNCTORS = {
 }
 
 
-def instantiate_preset(model, ncomp):
+def instantiate_preset(model, ncomp, full=False):
     """NVRTC instantiation of a hand-written preset functor for a component
     count that is not pre-compiled into libsdeb.so (e.g. a 7-factor
-    Hull-White).  Same engine, same functor source -- only the template
-    argument differs."""
+    Hull-White), or with full-resolution draws (``draws='full'``:
+    -DSDEB_DRAW_FULL=1).  Same engine, same functor source -- only the template
+    argument / the draw macro differ."""
     functor = PRESET_FUNCTORS[model] % ncomp
     src = '\n'.join([
         'namespace sdeb { typedef %s UserModel; }' % functor,
@@ -498,12 +499,13 @@ def instantiate_preset(model, ncomp):
         '    sdeb::UserModel::NW, sdeb::UserModel::NDW, sdeb::UserModel::NX,',
         '    sdeb::UserModel::NPC, sdeb::UserModel::NCNT, sdeb::UserModel::JUMPS};',
         ''] + JIT_ENTRIES)
-    return _compile(engine_source() + src, 'preset_%d_%d' % (model, ncomp))
+    return _compile(engine_source(full) + src, 'preset_%d_%d%s' % (model, ncomp, '_full'*full))
 
 
-def engine_source():
+def engine_source(full=False):
+    """The engine header; ``full``: 96 random bits per normal pair."""
     with open(os.path.join(HERE, 'csrc', 'sde_engine.cuh')) as f:
-        return f.read()
+        return ('#define SDEB_DRAW_FULL 1\n' if full else '') + f.read()
 
 
 class _traced:
@@ -574,7 +576,8 @@ class _traced:
         let = self._trace_let(t0)
         counters = self._trace_info()
         src = self._codegen(tr, roots, mil, let, counters)
-        handle = _compile(engine_source() + PRELUDE + src, type(self).__name__)
+        handle = _compile(engine_source(getattr(self, 'draws', 'fast') == 'full') + PRELUDE + src,
+                          type(self).__name__)
         self._jit = dict(handle=handle, sig=sig, nleaf=nleaf, milstein=milstein,
                          source=src, let=None if let is None else let[1],
                          counters=[k for k, _, _ in counters])

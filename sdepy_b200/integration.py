@@ -12,7 +12,9 @@ overridable ``sde / init / shapes / more / source_*`` hooks, ``method=`` and
 ``seed`` (Philox key), ``output`` ('process' host container -- the drop-in
 default --, 'device' HBM-resident container, 'stats' fused statistics only),
 ``device``, ``path_offset`` (global index of this shard's first path),
-``payoff``.  There is no CPU fallback.
+``payoff``, ``draws`` ('fast': 64 random bits per pair of normals, the default;
+'full': 96 bits, a 52-bit radius uniform like numpy's 53-bit ziggurat).  There
+is no CPU fallback.
 """
 import numpy as np
 import torch
@@ -405,7 +407,7 @@ class SDE(_jit._traced):
     def __init__(self, *, paths=1, vshape=(), dtype=None, rng=None,
                  steps=None, i0=0, info=None, getinfo=True, method='euler',
                  seed=None, output='process', device=None, path_offset=0,
-                 payoff=None, **args):
+                 payoff=None, draws='fast', **args):
         if not isinstance(self, integrator):
             raise TypeError(
                 'cannot instantiate SDE subclass {} that is not a subclass of '
@@ -417,6 +419,11 @@ class SDE(_jit._traced):
         if output not in ('process', 'device', 'stats'):
             raise ValueError("output must be 'process', 'device' or 'stats', "
                              'not {!r}'.format(output))
+        if draws not in ('fast', 'full'):
+            raise ValueError("draws must be 'fast' (64 random bits per pair of normals: "
+                             "32-bit radius uniform, 32-bit angle) or 'full' (96 bits: 52-bit "
+                             'radius uniform), not {!r}'.format(draws))
+        self.draws = draws
         self.output, self.device = output, device
         self.path_offset, self.payoff = int(path_offset), payoff
         self.vshape = _shape_setup(vshape)
@@ -971,6 +978,12 @@ class _preset_SDE(SDE):
     def _spec(self):
         lead, ncomp = self._lanes()
         groups = int(np.prod(lead, dtype=int))
+        if self.draws == 'full':
+            # full-resolution draws: the same functor compiled with
+            # -DSDEB_DRAW_FULL=1 (NVRTC, cached per model and component count)
+            handle = _jit.instantiate_preset(self._model, ncomp, full=True)
+            return _engine.problem_spec(_lib.MODEL_JIT, ncomp, groups,
+                                        jit_handle=handle), lead
         try:
             return _engine.problem_spec(self._model, ncomp, groups), lead
         except _lib.SdebError:

@@ -40,7 +40,7 @@ _COPIED = ('__module__', '__name__', '__qualname__', '__doc__')
 # keywords this package adds to the reference's constructors: reported by
 # ``params`` only when given, so that the parameter sets read like the
 # reference's
-_EXTENSIONS = ('seed', 'output', 'device', 'path_offset', 'payoff')
+_EXTENSIONS = ('seed', 'output', 'device', 'path_offset', 'payoff', 'draws')
 
 
 def _named_like(wrapped, wrapper):
