@@ -364,9 +364,10 @@ def test_full_resolution_draws_heston_price_and_stream_independence():
     fast = m.heston_process(paths=n, **kw)((0., 1.))
     pf, ef = (float(np.asarray(z)[-1, 0]) for z in (full.payoff_mean(), full.payoff_stderr()))
     assert abs(pf - 9.2425) < 4*ef + 1e-2
-    assert full.sums[-1, 0, 0] != fast.sums[-1, 0, 0]
+    assert full.sums[-1].ravel()[0] != fast.sums[-1].ravel()[0]
     a = m.heston_process(paths=n//4, draws='full', **kw)((0., 1.))
     b = m.heston_process(paths=n - n//4, path_offset=n//4, draws='full', **kw)((0., 1.))
-    assert np.allclose((a.sums + b.sums)[-1, 0, :4], full.sums[-1, 0, :4], rtol=1e-10, atol=1e-6)
+    assert np.allclose((a.sums + b.sums)[-1].ravel()[:4], full.sums[-1].ravel()[:4], rtol=1e-10,
+                       atol=1e-6)
     with pytest.raises(ValueError):
         m.heston_process(paths=10, draws='53bit')
