@@ -286,12 +286,32 @@ def full_path_modes(sd, torch, dev):
             output='device')(tlr)))
         for name, paths, steps, read, fn in cases:
             t = kernel_seconds(fn)
+            torch.cuda.empty_cache()
             nbytes = 8.*(paths*(steps + 1) + read)
             out[name] = {'paths': paths, 'steps': steps, 'kernel_s': t,
                          'path_steps_per_s': paths*steps/t,
                          'algorithmic_bytes': nbytes, 'GBps': nbytes/t/1e9,
                          'frac_of_hbm_peak': nbytes/t/1e9/peak}
         del dW
+        # the drop-in default: the same C2a run returned as a HOST process
+        # (output='process'): lowering + kernel + pinned D2H of the 4 GB slab
+        run = lambda: sd.ornstein_uhlenbeck_process(
+            x0=.1, theta=lambda s: .2 + .1*s, k=1., sigma=.3, paths=p, seed=2)(tl)
+        run()                                   # pins the host buffer
+        walls = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            xh = run()
+            walls.append(time.perf_counter() - t0)
+            del xh
+        slab = 8.*p*(n + 1)
+        out['C2a_e2e_process'] = {
+            'paths': p, 'steps': n, 'wall_s': min(walls),
+            'path_steps_per_s': p*n/min(walls), 'slab_bytes': slab,
+            'd2h_GBps_whole_call': slab/min(walls)/1e9,
+            'note': "output='process' (host ndarray subclass, the reference's return type): "
+                    'the call is the device-to-host copy of the slab over PCIe (~55 GB/s '
+                    'pinned); the kernel is ~2 % of it, so there is nothing to overlap'}
     finally:
         _lib.lib.sdeb_integrate = real
     out['hbm_peak_GBps'] = peak

@@ -676,17 +676,29 @@ class device_process:
     def psum(self):
         return self._wrap(self._moments()[:, 0])
 
+    def _two_pass(self):
+        """(first-pass mean, power sums about it): two HBM passes -- sum / min /
+        max, then the centred sums with the centre taken from the first pass ON
+        THE DEVICE -- and one device-to-host copy (two-pass accuracy of
+        numpy.mean / numpy.var, reference infrastructure.py:861-889)."""
+        rows, n = self._rows(), self.paths
+        rs_parts, st_parts = [], []
+        for r0 in range(0, rows.shape[0], 32768):
+            part = rows[r0:r0 + 32768]
+            rs = _cuda.mc_range(part, n)
+            st_parts.append(_cuda.mc_update(part, n, range_stats=rs))
+            rs_parts.append(rs)
+        both = torch.cat(rs_parts + st_parts).cpu().numpy()
+        k = rows.shape[0]
+        return both[:k, 0]/n, both[k:]
+
     def pmean(self):
-        m = self._moments()
-        c = m[:, 0]/self.paths
-        # second pass centred on the first-pass mean: two-pass accuracy
-        m2 = self._moments(centre=c)
+        c, m2 = self._two_pass()
         return self._wrap(c + m2[:, 0]/self.paths)
 
     def pvar(self, ddof=0):
         n = self.paths
-        c = self._moments()[:, 0]/n
-        m = self._moments(centre=c)
+        c, m = self._two_pass()
         d = m[:, 0]/n
         return self._wrap((m[:, 1] - n*d*d)/(n - ddof))
 
