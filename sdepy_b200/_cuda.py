@@ -39,6 +39,29 @@ def to_device(a, dev, dtype=None):
     return t.to(dev, non_blocking=True)
 
 
+def upload_packed(arrays, dev):
+    """Several small host arrays -> device tensors through ONE page-locked
+    staging buffer and ONE async H2D copy (the per-launch tables: steps, store
+    rows, parameter records, initial state, centre)."""
+    arrays = [np.ascontiguousarray(a) for a in arrays]
+    offs, at = [], 0
+    for a in arrays:
+        offs.append(at)
+        at += (a.nbytes + 15) & ~15
+    host = torch.empty(max(at, 16), dtype=torch.uint8, pin_memory=True)
+    hv = host.numpy()
+    for a, o in zip(arrays, offs):
+        if a.nbytes:
+            hv[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
+    d = host.to(dev, non_blocking=True)
+    out = []
+    for a, o in zip(arrays, offs):
+        t = d[o:o + a.nbytes].view(getattr(torch, a.dtype.name)).reshape(a.shape)
+        t._sdeb_staging = host           # keep the pinned block until the copy has run
+        out.append(t)
+    return out
+
+
 # Host copies of large results go through page-locked memory: a pageable
 # `.cpu()` of a full-path slab runs at ~2 GB/s, a pinned copy at ~57 GB/s
 # (torch's caching host allocator keeps the pinned block for the next call).

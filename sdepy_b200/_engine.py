@@ -137,10 +137,13 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
     stats_total = None
     w0 = np.ascontiguousarray(w0, dtype=float)
     w0_per_path = int(w0.ndim == 3)
-    w0_d = _cuda.to_device(w0, dev)
-    centre_d = None
-    if want_stats:
-        centre_d = _cuda.to_device(np.asarray(centre, dtype=float).reshape(gx), dev)
+    # small host tables travel in one page-locked staging buffer per sweep
+    centre_h = np.asarray(centre, dtype=float).reshape(gx) if want_stats else np.zeros(0)
+    small = w0.nbytes + centre_h.nbytes <= (1 << 20)
+    w0_d = centre_d = None
+    if not small:
+        w0_d = _cuda.to_device(w0, dev)
+        centre_d = _cuda.to_device(centre_h, dev) if want_stats else None
 
     keep = []   # keep device buffers alive until the launches are enqueued
     for k, seg in enumerate(segs):
@@ -163,10 +166,22 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
         p.w0_per_path = w0_per_path
         p.seed = (seed + seg.step_base*0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
         steps = np.stack((seg.ds, np.sqrt(np.abs(seg.ds))), axis=1) if n else np.zeros((0, 2))
-        steps_d = _cuda.to_device(steps, dev)
-        rows_d = _cuda.to_device(seg.store_row, dev, dtype=np.int32)
-        rec_d = _cuda.to_device(rec, dev)
-        keep += [steps_d, rows_d, rec_d]
+        if rec.nbytes <= (1 << 20):
+            tabs = [steps, np.asarray(seg.store_row, dtype=np.int32), rec]
+            if w0_d is None:
+                tabs += [w0, centre_h]
+            up = _cuda.upload_packed(tabs, dev)
+            steps_d, rows_d, rec_d = up[:3]
+            if w0_d is None:
+                w0_d, centre_d = up[3], (up[4] if want_stats else None)
+        else:
+            steps_d = _cuda.to_device(steps, dev)
+            rows_d = _cuda.to_device(seg.store_row, dev, dtype=np.int32)
+            rec_d = _cuda.to_device(rec, dev)
+            if w0_d is None:
+                w0_d = _cuda.to_device(w0, dev)
+                centre_d = _cuda.to_device(centre_h, dev) if want_stats else None
+        keep += [steps_d, rows_d, rec_d, w0_d, centre_d]
         p.steps, p.store_row = steps_d.data_ptr(), rows_d.data_ptr()
         p.params, p.w0 = rec_d.data_ptr(), w0_d.data_ptr()
         p.params_per_path = int(per_path)

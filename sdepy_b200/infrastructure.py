@@ -172,8 +172,22 @@ def _source_setup(dz, source_type, paths, vshape, **args):
 _empty = inspect.Signature.empty
 
 
+_SIGNATURES = {}
+
+
 def _signature(f):
-    return [(k, p.default) for k, p in inspect.signature(f).parameters.items()]
+    """[(name, default)] of f's parameters; cached per function (a process is
+    constructed at every Monte Carlo batch: inspect.signature is 40 us a call)."""
+    key = (getattr(f, '__func__', f), getattr(f, '__self__', None) is not None)
+    try:
+        sig = _SIGNATURES.get(key)
+    except TypeError:                    # unhashable callable
+        key, sig = None, None
+    if sig is None:
+        sig = tuple((k, p.default) for k, p in inspect.signature(f).parameters.items())
+        if key is not None:
+            _SIGNATURES[key] = sig
+    return list(sig)
 
 
 # --------------------------------------------------------------------------
