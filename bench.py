@@ -312,6 +312,19 @@ def full_path_modes(sd, torch, dev):
             'note': "output='process' (host ndarray subclass, the reference's return type): "
                     'the call is the device-to-host copy of the slab over PCIe (~55 GB/s '
                     'pinned); the kernel is ~2 % of it, so there is nothing to overlap'}
+        # price of the full-resolution draw option on the headline workload
+        # (96 instead of 64 random bits per pair of normals; NVRTC-compiled)
+        grid = np.linspace(0., 1., N_STEPS + 1)
+        res = {}
+        for tag in ('fast', 'full'):
+            P = sd.heston_process(paths=10_000_000, steps=grid, rho=RHO, seed=1, output='stats',
+                                  draws=tag, getinfo=False, **HESTON)
+            res[tag] = 10_000_000*N_STEPS/kernel_seconds(lambda: P((0., 1.)))
+        out['heston_draws_full'] = {
+            'paths': 10_000_000, 'steps': N_STEPS, 'path_steps_per_s_fast': res['fast'],
+            'path_steps_per_s_full': res['full'], 'full_over_fast': res['full']/res['fast'],
+            'note': "draws='full': 52-bit radius uniform + 32-bit angle, one Philox block per "
+                    'pair (default: 32 + 32 bits, two pairs per block)'}
     finally:
         _lib.lib.sdeb_integrate = real
     out['hbm_peak_GBps'] = peak
