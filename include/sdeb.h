@@ -112,7 +112,8 @@ typedef struct sdeb_problem {
     const double* w0;         /* initial WORKING state (after init/log,
                                  integration.py:1161-1164): [n_groups][nw] (+[pitch]) */
     const double* dW;         /* replay: [n_steps][n_groups*ndw][pitch]         */
-    const double* dJ;         /* replay: [n_steps][n_groups*nw][pitch]          */
+    const double* dJ;         /* replay: [n_steps][n_groups*jumps*nw][pitch] (jump slot
+                                 s, component c at lane s*nw + c)                  */
     const int64_t* dN;        /* replay: same layout, optional                  */
     double* out;              /* [n_rows][n_groups*nx][pitch], may be NULL; elements
                                  of type out_dtype (float64 unless stated)         */
@@ -152,7 +153,8 @@ typedef struct sdeb_plan_t {
                                  lower Cholesky factor of corr (identity if none),
                                  used by the Philox draws (infrastructure.py:1532) */
     int64_t ncnt;             /* counters per lane                              */
-    int64_t jumps;            /* model has a compound-Poisson term              */
+    int64_t jumps;            /* compound-Poisson terms per component: 0, 1, or 2 (a
+                                 traced model with both 'dj' and 'dn' differentials) */
     int64_t blocks;           /* grid size that will be launched                */
     int64_t threads;          /* block size                                     */
     int64_t smem_bytes;       /* dynamic shared memory per block                */

@@ -64,6 +64,7 @@ class problem_spec:
         self.nw, self.ndw, self.nx = plan.nw, plan.ndw, plan.nx
         self.npc, self.npt, self.ncnt = plan.npc, plan.npt, plan.ncnt
         self.jumps = bool(plan.jumps)
+        self.njw = self.nw*max(int(plan.jumps), 1)    # jump lanes: slots x components
         self.nchol = self.npt - self.npc
 
 
@@ -127,8 +128,15 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
                if want_out else None)
     if want_out:
         # rows never reached stay NaN, like the reference's allocation
-        # (integration.py:550)
-        res.out.fill_(float('nan'))
+        # (integration.py:550); when the sweeps store every row the prefill
+        # would only double the HBM write traffic of a full-path run
+        reached = np.zeros(n_rows, dtype=bool)
+        for k, seg in enumerate(segs):
+            if k == 0 and 0 <= seg.row0 < n_rows:
+                reached[seg.row0] = True
+            reached[seg.store_row[seg.store_row >= 0]] = True
+        if not (reached.all() and paths > 0):
+            res.out.fill_(float('nan'))
     res.stats = None
     # (zeroed at the start of every sweep, below)
     res.counter = (_cuda.empty((spec.groups*spec.ncnt, paths), dev, torch.int64)
@@ -204,12 +212,12 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
                 if t.dtype != want:
                     t = t.to(want)
                 t = t.contiguous()
-                if t.numel() != n*spec.groups*(spec.ndw if name == 'dW' else spec.nw)*paths:
+                if t.numel() != n*spec.groups*(spec.ndw if name == 'dW' else spec.njw)*paths:
                     raise ValueError(
                         'replay table {} has {} elements, expected steps x '
                         'lanes x paths = {} x {} x {}'.format(
                             name, t.numel(), n,
-                            spec.groups*(spec.ndw if name == 'dW' else spec.nw), paths))
+                            spec.groups*(spec.ndw if name == 'dW' else spec.njw), paths))
                 keep.append(t)
                 setattr(p, name, t.data_ptr())
         if want_out:
@@ -227,8 +235,8 @@ def run(spec, segs, n_rows, records, w0, *, paths, path_offset=0, seed=0,
             d = {'dW': _cuda.empty((n, spec.groups*spec.ndw, paths), dev)}
             p.dW_dump = d['dW'].data_ptr()
             if spec.jumps:
-                d['dJ'] = _cuda.empty((n, spec.groups*spec.nw, paths), dev)
-                d['dN'] = _cuda.empty((n, spec.groups*spec.nw, paths), dev, torch.int64)
+                d['dJ'] = _cuda.empty((n, spec.groups*spec.njw, paths), dev)
+                d['dN'] = _cuda.empty((n, spec.groups*spec.njw, paths), dev, torch.int64)
                 p.dJ_dump, p.dN_dump = d['dJ'].data_ptr(), d['dN'].data_ptr()
             res.dump.append(d)
         p.max_blocks = max_blocks

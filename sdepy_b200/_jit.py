@@ -681,7 +681,7 @@ class _traced:
 
     def _records(self, spec, seg, lead, replay):
         jit = self._jit
-        dw, dj = self.sources.get('dw'), self._jump_source()
+        dw = self.sources.get('dw')
         lanes = self._param_target()
         # is anything time-dependent?  (callable parameters, explicit use of t)
         probe = [float(seg.s[0]), float(seg.s[-1])] if seg.n_steps else [0.]
@@ -703,23 +703,23 @@ class _traced:
             cols = [lane_values(v, lanes, 'SDE parameter', paths=self.paths) for v in leaves]
             block = (stack_lane_columns(cols, spec.groups, elems) if cols
                      else np.zeros((spec.groups, 0)))
-            if spec.jumps:
-                block = _join_blocks(block, self._jump_block(spec, dj, s, ds, replay))
+            for id, src in self._jump_slots():
+                block = _join_blocks(block, self._jump_block(spec, id, src, s, ds, replay))
             L = None
             if spec.nchol and not replay and isinstance(dw, wiener_source):
                 L = dw.chol_at(s + ds/2)
             blocks.append((block, _engine.chol_entries(L, spec.ndw)))
         return _engine.assemble_records(blocks, spec)
 
-    def _jump_block(self, spec, dj, s, ds, replay):
-        """[groups, 6*nw (, paths)]: per working component lam, (reserved), law,
-        a, b, pa -- intensity and law sampled at the step midpoint
-        (infrastructure.py:1630, 2031)."""
+    def _jump_block(self, spec, id, dj, s, ds, replay):
+        """[groups, 6*nw (, paths)] of ONE jump slot: per working component lam,
+        (reserved), law, a, b, pa -- intensity and law sampled at the step
+        midpoint (infrastructure.py:1630, 2031)."""
         nw = spec.nw
         if replay:
             return np.zeros((spec.groups, 6*nw))
         mid = s + ds/2
-        if 'dn' in self.sources:         # plain Poisson: unit jump sizes
+        if id == 'dn':                   # plain Poisson: unit jump sizes
             lam_src = dj
             kind, a, b, pa = _lib.LAW_UNIFORM, 1., 1., 0.
         else:
@@ -755,7 +755,8 @@ class _traced:
         if unknown:
             raise NotImplementedError('differentials {} have no device '
                                       'implementation'.format(unknown))
-        jumps = self._jump_source() is not None
+        slot_of = {id: k for k, (id, _) in enumerate(self._jump_slots())}
+        jumps = len(slot_of)             # jump slots: 'dj' and / or 'dn'
         nleaf = len(tr.leaves)
 
         def comp(k):
@@ -766,8 +767,8 @@ class _traced:
         for k, r in enumerate(roots):
             terms = []
             for ident, nd in r:
-                dz = {'dt': 'ds', 'dw': 'dw[%s]' % comp(k), 'dj': 'dj[%s]' % comp(k),
-                      'dn': 'dj[%s]' % comp(k)}[ident]
+                dz = ('ds' if ident == 'dt' else 'dw[%s]' % comp(k) if ident == 'dw' else
+                      'dj[%d + %s]' % (slot_of[ident]*nw, comp(k)))
                 terms.append('xmul(%s, %s)' % (em.ref(nd), dz))
             inc = terms[0] if terms else '0.0'
             for tm in terms[1:]:
@@ -784,7 +785,7 @@ class _traced:
                             .format(k, em.ref(mil[k]), comp(k)))
         # info_next counters (integer-valued expressions of the state before /
         # after the step), one per accumulation and element
-        base = nw if jumps else 0
+        base = nw*jumps
         pre, post = [], []
         for j, (key, ctr, nd) in enumerate(counters):
             uses_new = _uses_vars(nd, range(q, 2*q))
@@ -796,7 +797,7 @@ class _traced:
         body = pre + body + post
         for k in range(q):
             body.append('x[%s] = xn%d;' % (comp(k), k))
-        npc = elems*nleaf + (6*nw if jumps else 0)
+        npc = elems*nleaf + 6*nw*jumps
         ncnt = base + len(counters)*elems
         # user let(): emit() body
         emit, nx = None, nw
@@ -821,7 +822,7 @@ class _traced:
             return
         lead, nw = self._lanes()
         elems = nw//self._nvars
-        base = nw if self._jump_source() is not None else 0
+        base = nw*len(self._jump_slots())
         c = res.counter.reshape((-1, base + len(keys)*elems, self.paths))
         for j, key in enumerate(keys):
             part = c[:, base + j*elems:base + (j + 1)*elems, :]
@@ -873,7 +874,7 @@ def _join_blocks(a, b):
 
 def _model_source(nw, ndw, npc, jumps, jp_stride, jp_off, body, log, elems, ncnt=None,
                   nx=None, emit=None):
-    ncnt = (nw if jumps else 0) if ncnt is None else ncnt
+    ncnt = nw*int(jumps) if ncnt is None else ncnt
     nx = nw if nx is None else nx
     lines = ['namespace sdeb {', 'struct UserModel {',
              '    enum { NW = %d, NDW = %d, NX = %d, NPC = %d, NCNT = %d, JUMPS = %d,'

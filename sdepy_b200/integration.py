@@ -588,63 +588,98 @@ class SDE(_jit._traced):
         1233) -- and fed to the kernel in replay mode.  That covers replay
         tables, the reference's own source objects and ``process`` instances.
         """
-        dw, dj = self.sources.get('dw'), self._jump_source()
+        dw, slots = self.sources.get('dw'), self._jump_slots()
+        jsrc = [z for _, z in slots]
         unknown = set(self.sources) - {'dt', 'dw', 'dj', 'dn'}
         if unknown:
             raise NotImplementedError(
                 'sources {} have no device implementation'.format(unknown))
-        philox_ok = (dw is None or type(dw) in (wiener_source, odd_wiener_source)) and (
-            dj is None or
-            (type(dj) in (cpoisson_source, even_cpoisson_source) and dj.device_ready()) or
-            type(dj) in (poisson_source, even_poisson_source))
+        philox_ok = (dw is None or type(dw) in (wiener_source, odd_wiener_source)) and all(
+            (type(z) in (cpoisson_source, even_cpoisson_source) and z.device_ready()) or
+            type(z) in (poisson_source, even_poisson_source) for z in jsrc)
         if philox_ok:
             return None
+        # tables per sweep: 'dW' array, 'dJ' LIST of arrays (one per jump slot:
+        # 'dj' then 'dn'), 'dN' array (single slot exposing its counts)
         tables = []
-        if all(isinstance(z, replay_source) for z in (dw, dj) if z is not None):
+        if all(isinstance(z, replay_source) for z in [dw] + jsrc if z is not None):
             # whole tables at once (no per-step host calls, no copies)
             at = 0
             for seg in segs:
                 n = seg.n_steps
                 tab = {'dW': dw.table[at:at + n]} if dw is not None else {
                     'dW': np.zeros((n,) + self.wshape + (self.paths,))}
-                if dj is not None:
-                    tab['dJ'] = dj.table[at:at + n]
-                    if dj.dn_table is not None:
-                        tab['dN'] = dj.dn_table[at:at + n]
+                if jsrc:
+                    tab['dJ'] = [z.table[at:at + n] for z in jsrc]
+                    if len(jsrc) == 1 and jsrc[0].dn_table is not None:
+                        tab['dN'] = jsrc[0].dn_table[at:at + n]
                 for k, v in tab.items():
-                    if v.shape[0] != n:
-                        raise ValueError(
-                            'replay table {} holds {} steps, {} needed'
-                            .format(k, v.shape[0], n))
+                    for u in (v if isinstance(v, list) else [v]):
+                        if u.shape[0] != n:
+                            raise ValueError(
+                                'replay table {} holds {} steps, {} needed'
+                                .format(k, u.shape[0], n))
                 tables.append(tab)
                 at += n
             return tables
+        by_id = dict(slots)
         for seg in segs:
-            rows = {'dW': [], 'dJ': [], 'dN': []}
+            rows = {'dW': [], 'dN': []}
+            jrows = {id: [] for id, _ in slots}
             for s, ds in zip(seg.s, seg.ds):
                 for id in self._ordered_source_ids:
-                    if id in ('dj', 'dn'):
-                        z = dj(s, ds)
-                        rows['dJ'].append(self._as_lane_table(z))
-                        if hasattr(dj, 'dn_value'):
-                            rows['dN'].append(self._as_lane_table(dj.dn_value, integer=True))
+                    if id in by_id:
+                        z = by_id[id](s, ds)
+                        jrows[id].append(self._as_lane_table(z))
+                        if len(slots) == 1 and hasattr(by_id[id], 'dn_value'):
+                            rows['dN'].append(self._as_lane_table(by_id[id].dn_value, integer=True))
                     elif id == 'dw':
                         # device-resident sources hand over CUDA tensors
                         call = getattr(dw, 'device_call', dw)
                         rows['dW'].append(self._as_lane_table(call(s, ds)))
-            tab = {}
-            for k, v in rows.items():
-                if v:
-                    tab[k] = (torch.stack(v) if isinstance(v[0], torch.Tensor)
-                              else np.stack(v))
+
+            def stacked(v):
+                return torch.stack(v) if isinstance(v[0], torch.Tensor) else np.stack(v)
+            tab = {k: stacked(v) for k, v in rows.items() if v}
             # no Wiener term, or a sweep without steps (single-point timeline)
             empty = (seg.n_steps,) + self.wshape + (self.paths,)
             if 'dW' not in tab:
                 tab['dW'] = np.zeros(empty)
-            if dj is not None and 'dJ' not in tab:
-                tab['dJ'] = np.zeros(empty)
+            if slots:
+                tab['dJ'] = [stacked(jrows[id]) if jrows[id] else np.zeros(empty)
+                             for id, _ in slots]
             tables.append(tab)
         return tables
+
+    def _lane_tables(self, tab, seg, spec):
+        """Replay tables of one sweep in the kernel's layout [steps, lanes, paths];
+        jump tables of several slots are interleaved per lane group:
+        [steps, groups, slot, nw, paths]."""
+        n, paths = seg.n_steps, self.paths
+
+        def lanes(v):
+            return self._to_lanes(v, 1).reshape((n, -1 if n else 0, paths))
+        out = {}
+        for k, v in tab.items():
+            if not isinstance(v, list):
+                out[k] = lanes(v)
+            elif len(v) == 1:
+                out[k] = lanes(v[0])
+            else:
+                parts = [lanes(u) for u in v]
+                if any(isinstance(u, torch.Tensor) for u in parts):
+                    parts = [u if isinstance(u, torch.Tensor) else torch.from_numpy(
+                        np.ascontiguousarray(u)).to(next(
+                            w for w in parts if isinstance(w, torch.Tensor)).device)
+                        for u in parts]
+                    parts = [u.to(torch.float64).reshape((n, spec.groups, spec.nw, paths))
+                             for u in parts]
+                    out[k] = torch.stack(parts, dim=2).reshape((n, -1, paths))
+                else:
+                    parts = [np.asarray(u, dtype=float).reshape((n, spec.groups, spec.nw, paths))
+                             for u in parts]
+                    out[k] = np.stack(parts, axis=2).reshape((n, -1, paths))
+        return out
 
     def _as_lane_table(self, z, integer=False):
         shape = self.wshape + (self.paths,)
@@ -655,23 +690,26 @@ class SDE(_jit._traced):
             z = z.astype(np.int64)
         return np.broadcast_to(z, shape)
 
+    def _jump_slots(self):
+        """[(id, source)] feeding the kernel's jump slots, in sorted-id order
+        like the reference's calls (integration.py:1135): the compound Poisson
+        source 'dj' and / or a plain Poisson source 'dn' (unit jump sizes)."""
+        return [(id, self.sources[id]) for id in ('dj', 'dn') if id in self.sources]
+
     def _jump_source(self):
-        """The source feeding the kernel's jump slot: the compound Poisson
-        source 'dj', or a plain Poisson source 'dn' (unit jump sizes)."""
-        if 'dj' in self.sources and 'dn' in self.sources:
-            raise NotImplementedError(
-                "an SDE with both 'dn' and 'dj' differentials has no device "
-                'implementation')
-        return self.sources.get('dj', self.sources.get('dn'))
+        slots = self._jump_slots()
+        return slots[0][1] if slots else None
 
     def _jumps_time_dependent(self):
-        """True when the jump intensity or the jump-size law change in time
-        (both are sampled at step midpoints, infrastructure.py:1630, 2031)."""
-        dj = self._jump_source()
-        lam_src = getattr(dj, 'dn', dj)
-        law = getattr(dj, 'y', None)
-        return callable(getattr(lam_src, 'lam', None)) or any(
-            callable(z) for z in getattr(law, 'params', {}).values())
+        """True when a jump intensity or jump-size law changes in time (both
+        are sampled at step midpoints, infrastructure.py:1630, 2031)."""
+        for _, dj in self._jump_slots():
+            lam_src = getattr(dj, 'dn', dj)
+            law = getattr(dj, 'y', None)
+            if callable(getattr(lam_src, 'lam', None)) or any(
+                    callable(z) for z in getattr(law, 'params', {}).values()):
+                return True
+        return False
 
     def _philox_key(self):
         for id in ('dw', 'dj', 'dn'):
@@ -714,9 +752,7 @@ class SDE(_jit._traced):
                        for seg in segs]
             self._lowered = (key, (w0l, w0_arg, records))
         if replay is not None:
-            replay = [{k: self._to_lanes(v, 1).reshape(
-                           (seg.n_steps, -1 if seg.n_steps else 0, self.paths))
-                       for k, v in tab.items()} for tab, seg in zip(replay, segs)]
+            replay = [self._lane_tables(tab, seg, spec) for tab, seg in zip(replay, segs)]
         want_stats = self.output == 'stats'
         centre = self._stats_centre(w0l) if want_stats else None
         jumps = spec.jumps

@@ -138,3 +138,9 @@ def user_hooks_system(m):
     class B(B_SDE, m.integrator):
         pass
     return B
+
+
+def two_jump_terms(t, x, a=.5, b=.3, c=.2):
+    """One equation with a Poisson ('dn') AND a compound Poisson ('dj') term
+    next to drift and diffusion: two independent jump sources."""
+    return {'dt': -a*x, 'dw': b, 'dn': c*x, 'dj': 1.}

@@ -434,3 +434,43 @@ def test_user_let_and_info_hooks_bit_exact_vs_reference():
     # getinfo=False: no counters, same paths
     P = B(dw=m.replay_source(g['b_dW']), getinfo=False, **kw)
     assert np.array_equal(np.asarray(P(g['b_tt'])), g['b_out']) and 'ylow' not in P.info
+
+
+def test_sde_with_both_dn_and_dj_terms():
+    """An equation with a Poisson ('dn') AND a compound Poisson ('dj') term (two
+    jump slots in the kernel).  Replay of the reference's own recorded increments
+    (tests/golden/make_two_jump_terms.py) bit for bit; in Philox mode the two
+    sources are independent streams and the mean follows
+    m' = (c lam - a) m + lam E[y]."""
+    from tests.cases import golden, two_jump_terms
+    import sdepy_b200 as m
+    g = golden('replay_two_jump_terms')
+    cls = m.integrate(two_jump_terms)
+    assert set(cls.sources) == {'dt', 'dw', 'dn', 'dj'}
+    kw = dict(paths=31, vshape=(2,), steps=25, x0=1., a=g['p_a'])
+    P = cls(dw=m.replay_source(g['dW']), dn=m.replay_source(g['dN'].astype(float)),
+            dj=m.replay_source(g['dJ']), **kw)
+    x = P(g['tt'])
+    assert np.array_equal(np.asarray(x), g['out'])
+    # Philox mode
+    a, c, lam, ya = .5, .2, 3., -.1
+    paths = 400_000
+    Q = cls(paths=paths, steps=401, x0=1., a=a, c=c, lam=lam, y=m.norm_rv(a=ya, b=.2), seed=21,
+            output='stats')
+    st = Q((0., 1.))
+    r = c*lam - a
+    want = np.exp(r) + lam*ya*(np.exp(r) - 1)/r
+    got, err = float(np.asarray(st.pmean())[-1, 0]), float(np.asarray(st.stderr())[-1, 0])
+    assert abs(got - want) < 4*err + 2e-3, (got, want, err)
+    # the two jump sources are distinct streams: dumped increments
+    D = cls(paths=20_000, steps=51, x0=1., lam=lam, y=m.norm_rv(a=ya, b=.2), seed=22)
+    D._dump_increments = True
+    D((0., 1.))
+    d = D._last_run.dump[0]
+    dj, dn = d['dJ'].cpu().numpy().reshape(50, 2, -1)[:, 0], d['dJ'].cpu().numpy().reshape(50, 2, -1)[:, 1]
+    cn = d['dN'].cpu().numpy().reshape(50, 2, -1)
+    assert np.array_equal(dn, cn[:, 1].astype(float))            # 'dn' slot: unit jumps
+    assert abs(cn[:, 0].mean() - lam/50) < 5*np.sqrt(lam/50/cn[:, 0].size)
+    assert abs(cn[:, 1].mean() - lam/50) < 5*np.sqrt(lam/50/cn[:, 1].size)
+    assert not np.array_equal(cn[:, 0], cn[:, 1])
+    assert abs(dj.sum()/max(cn[:, 0].sum(), 1) - ya) < 5*.2/np.sqrt(max(cn[:, 0].sum(), 1))
