@@ -90,15 +90,21 @@ typedef struct sdeb_problem {
                                  vary along the paths axis, e.g. process-valued ones) */
     uint64_t seed;            /* Philox4x32-10 key.  Counter = (global path low 32
                                  bits, path bits 32..39 | group << 8, step word,
-                                 stream | component << 16).  Normals: step word =
+                                 stream | jump lane << 16).  Normals: step word =
                                  n / P with P in {1, 2, 4} the number of steps that
                                  consume whole blocks (a block = two Box-Muller pairs
-                                 of 64 bits), stream = block index; Poisson counts:
-                                 step word = even step, stream 0x100; jump sizes:
-                                 stream 0x200 + j; exponent extension of a pair
-                                 (probability 2^-12): stream 0x8000 + pair.  Results
-                                 depend on (seed, global path, group) only -- not on
-                                 the sharding, the grid or the launch geometry     */
+                                 of 64 bits: 32-bit radius uniform + 32-bit angle; one
+                                 pair of 96 bits in kernels compiled with
+                                 -DSDEB_DRAW_FULL=1), stream = block index; Poisson
+                                 counts: step word = even step, stream 0x100 (further
+                                 blocks 0x4000 + j when lam|dt| > 30 and the draw is
+                                 split into Poisson(lam|dt|/m) terms); jump sizes:
+                                 stream 0x200 + j.  Results depend on (seed, global
+                                 path, group) only -- not on the sharding, the grid or
+                                 the launch geometry; the lean kernel (sdeb_plan_t.kernel
+                                 == 1: Philox, one time-invariant record) contracts its
+                                 step arithmetic into FMAs and agrees with the other
+                                 two to rounding level (~1e-14 over a few hundred steps) */
     const double* steps;      /* [n_steps][2]: dt = t[n+1]-t[n] (integration.py:714),
                                  sqrt|dt| (infrastructure.py:1558-1559)         */
     const int32_t* store_row; /* [n_steps]: row storing the state after step n
