@@ -227,10 +227,13 @@ def measured_hbm_peak():
         return 6553.6, 'fallback of B200_PROFILING.md (no MEASURED_PEAKS.json)'
 
 
-def full_path_modes(sd, torch, dev):
+def full_path_modes(sd, torch, dev, rank=0, world=1, dist=None):
     """The HBM-bound output mode: full paths stored time-major [steps, vars,
     paths] in HBM (output='device').  Kernel time = CUDA events around
-    sdeb_integrate on the launching stream (best of 3 after one warm-up)."""
+    sdeb_integrate on the launching stream (best of 3 after one warm-up).  At
+    N > 1 every rank runs the three kernel cases on its own shard of paths at
+    the same time (barrier before each) and the figures are the aggregate over
+    the ranks at the MAX of their times; the host-facing rows run on rank 0."""
     from sdepy_b200 import _lib
     peak, src = measured_hbm_peak()
     events = []
@@ -285,14 +288,23 @@ def full_path_modes(sd, torch, dev):
             x0=.1, theta=.2, k=1., sigma=.3, paths=pr, dw=sd.replay_source(dW),
             output='device')(tlr)))
         for name, paths, steps, read, fn in cases:
+            if world > 1:
+                dist.barrier()
             t = kernel_seconds(fn)
             torch.cuda.empty_cache()
+            if world > 1:
+                tt_ = torch.tensor([t], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+                t = float(tt_[0])
             nbytes = 8.*(paths*(steps + 1) + read)
-            out[name] = {'paths': paths, 'steps': steps, 'kernel_s': t,
-                         'path_steps_per_s': paths*steps/t,
-                         'algorithmic_bytes': nbytes, 'GBps': nbytes/t/1e9,
+            out[name] = {'paths_per_gpu': paths, 'steps': steps, 'kernel_s': t,
+                         'path_steps_per_s': world*paths*steps/t,
+                         'algorithmic_bytes_per_gpu': nbytes, 'GBps': world*nbytes/t/1e9,
+                         'GBps_per_gpu': nbytes/t/1e9,
                          'frac_of_hbm_peak': nbytes/t/1e9/peak}
         del dW
+        if rank != 0:
+            return None
         # the drop-in default: the same C2a run returned as a HOST process
         # (output='process'): lowering + kernel + pinned D2H of the 4 GB slab
         run = lambda: sd.ornstein_uhlenbeck_process(
@@ -329,9 +341,12 @@ def full_path_modes(sd, torch, dev):
         _lib.lib.sdeb_integrate = real
     out['hbm_peak_GBps'] = peak
     out['hbm_peak_source'] = src
+    out['n_gpus'] = world
     out['note'] = ('full-path output mode, stored rows [steps+1, paths] fp64 in HBM; '
                    'algorithmic bytes = 8 B per stored value (+ 8 B per replayed increment); '
-                   'the Philox rows are FP64-issue bound (draws), replay_ou is the HBM-bound one')
+                   'the Philox rows are FP64-issue bound (draws), replay_ou is the HBM-bound one; '
+                   'at N > 1 all ranks run at once: GBps and path_steps_per_s are aggregates '
+                   'at the max of the ranks\' times, frac_of_hbm_peak is per GPU')
     return out
 
 
@@ -483,7 +498,7 @@ def run_ours(a):
                     'weak line) / (N x T(N GPUs))' % (paths, world, paths)}
 
     # ---- the other configurations, under the same driver run ---------------
-    modes = full_path_modes(sd, torch, dev) if rank == 0 else None
+    modes = full_path_modes(sd, torch, dev, rank, world, dist)
     barrier()
     c5 = c5_allreduce_check(sd, torch, dist, rank, world, dev)
     # per step: steps table, store rows, parameter record, initial state, centre

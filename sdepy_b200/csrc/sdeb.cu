@@ -113,11 +113,14 @@ static int64_t smem_bytes(const ModelInfo& mi, const sdeb_problem* p, bool stats
 // everything to the general kernel (used by the tests to compare the two).
 static bool aligned16(const void* q) { return (((uintptr_t)q) & 15) == 0; }
 static bool stream_shape(const sdeb_problem* p, const ModelInfo& mi) {
-    if (mi.jumps || !p->out || p->stats || p->out_dtype != 0 || p->params_per_path ||
+    if ((mi.jumps && p->noise != SDEB_NOISE_REPLAY) || !p->out || p->stats ||
+        p->out_dtype != 0 || p->params_per_path ||
         p->dW_dump || p->dJ_dump || p->dN_dump || p->anti_dw_half || p->anti_dj_half ||
         (p->pitch & 1) || !aligned16(p->out) || p->n_steps < 1)
         return false;
-    if (p->noise == SDEB_NOISE_REPLAY && !aligned16(p->dW)) return false;
+    if (p->noise == SDEB_NOISE_REPLAY &&
+        (!aligned16(p->dW) || (mi.jumps && (!aligned16(p->dJ) || !aligned16(p->dN)))))
+        return false;
     const char* off = getenv("SDEB_NO_STREAM");
     return !(off && off[0] == '1');
 }
@@ -129,7 +132,10 @@ static int64_t stream_smem_bytes(const ModelInfo& mi, const sdeb_problem* p) {
     int64_t d = 0;
     if (p->noise != SDEB_NOISE_REPLAY) d += (int64_t)TAB_DOUBLES * SDEB_TAB_COPIES;
     if (p->n_psteps > 1) d += (int64_t)STEP_CHUNK * ((mi.npc + nch + 1) & ~(int64_t)1);
-    if (p->noise == SDEB_NOISE_REPLAY) d += (int64_t)stream_depth(mi.ndw) * mi.ndw * kThreads * 2;
+    if (p->noise == SDEB_NOISE_REPLAY) {
+        const int64_t ne = mi.ndw + (mi.jumps ? 2 * (int64_t)mi.jumps * mi.nw : 0);
+        d += (int64_t)stream_depth((int)ne) * ne * kThreads * 2;
+    }
     return d * 8;
 }
 

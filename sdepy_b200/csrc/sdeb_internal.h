@@ -10,7 +10,7 @@ struct ModelInfo {
     const void* fn;        // general kernel
     const void* fn_lean;   // hot-configuration kernel (may be NULL)
     const void* fn_stream[4];   // full-path stream kernel [2*replay + time-dependent records]
-                                // (NULL for jump models)
+                                // (jump models: replay variants only)
     int nw, ndw, nx, npc, ncnt, jumps;
 };
 
@@ -23,9 +23,9 @@ static ModelInfo info_of() {
     if constexpr (M::JUMPS == 0) {
         mi.fn_stream[0] = (const void*)&sdeb::stream_kernel<M, sdeb::NOISE_PHILOX, false>;
         mi.fn_stream[1] = (const void*)&sdeb::stream_kernel<M, sdeb::NOISE_PHILOX, true>;
-        mi.fn_stream[2] = (const void*)&sdeb::stream_kernel<M, sdeb::NOISE_REPLAY, false>;
-        mi.fn_stream[3] = (const void*)&sdeb::stream_kernel<M, sdeb::NOISE_REPLAY, true>;
     }
+    mi.fn_stream[2] = (const void*)&sdeb::stream_kernel<M, sdeb::NOISE_REPLAY, false>;
+    mi.fn_stream[3] = (const void*)&sdeb::stream_kernel<M, sdeb::NOISE_REPLAY, true>;
     mi.nw = M::NW; mi.ndw = M::NDW; mi.nx = M::NX; mi.npc = M::NPC;
     mi.ncnt = M::NCNT; mi.jumps = M::JUMPS;
     return mi;

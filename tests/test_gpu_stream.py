@@ -149,3 +149,36 @@ def test_jump_models_and_odd_pitch_keep_the_general_kernel():
         P._trace_kernels = True
         P(tl)
         assert KERNEL_STREAM not in P._last_run.kernels
+
+
+@pytest.mark.parametrize('kind', ['merton', 'kou'])
+def test_stream_replays_jump_models(kind):
+    """Replayed jump-diffusions take the stream kernel too (dJ and the dN counts
+    ride the cp.async ring next to dW): same paths, jump counts and jump rates
+    as the general kernel, and the oracle's paths within 4 ulp."""
+    from oracle import sde_oracle as orc
+    m = sd()
+    paths, n = 2000, 150
+    grid = np.linspace(0., 1., n + 1)
+    par = dict(mu=.05, sigma=.2)
+    if kind == 'merton':
+        law, cls, lkw = orc.jump_law('norm', a=-.1, b=.15), m.merton_jumpdiff_process, dict(a=-.1, b=.15)
+    else:
+        law, cls = orc.jump_law('double_exp', a=.1, b=.15, pa=.4), m.kou_jumpdiff_process
+        lkw = dict(a=.1, b=.15, pa=.4)
+    rng = np.random.default_rng(17)
+    dW = np.empty((n, paths)); dJ = np.empty((n, paths)); dN = np.empty((n, paths), dtype=np.int64)
+    for i in range(n):
+        s, ds = grid[i], grid[i + 1] - grid[i]
+        dJ[i], dN[i] = orc.draw_cpoisson(rng, s, ds, (), paths, 4., law)
+        dW[i] = orc.draw_wiener(rng, s, ds, (), paths)
+    where = list(range(0, n + 1, 10))
+    (xs, Ps), (xg, Pg) = both(lambda: cls(
+        paths=paths, steps=grid, x0=1., lam=4., dw=m.replay_source(dW),
+        dj=m.replay_source(dJ, dn=dN), output='device', **par, **lkw), grid[where])
+    same(xs, xg)
+    assert torch.equal(Ps.info['jump_count'], Pg.info['jump_count'])
+    assert np.array_equal(Ps.info['jump_rate'], Pg.info['jump_rate'])
+    want, winfo = orc.euler_replay('jumpdiff', par, 1., grid, where, dW, dJ=dJ, dN=dN)
+    assert np.abs(xs.x.cpu().numpy()/want - 1).max() <= 4*np.finfo(float).eps
+    assert np.array_equal(Ps.info['jump_count'].cpu().numpy(), winfo['jump_count'])

@@ -158,6 +158,18 @@ def main():
         x0=1., mu=.05, sigma=.2, lam=2., a=-.1, b=.15, paths=p, steps=n + 1, seed=5,
         output='stats')((0., 1.)))
     rec('C4 merton terminal stats (philox, getinfo: jump_count + jump_rate)', p, n, t)
+    # C4 in REPLAY mode at its own step count: dW + dJ + dN tables streamed from HBM
+    # (24 B read per path-step), terminal value only
+    p, n = int(1_000_000*a.scale), 1000
+    g = torch.Generator(device='cuda'); g.manual_seed(1)
+    dW = torch.randn((n, p), dtype=torch.float64, device='cuda', generator=g)*np.sqrt(1/n)
+    dN = torch.poisson(torch.full((n, p), 2./n, dtype=torch.float64, device='cuda'), generator=g).to(torch.int64)
+    dJ = dN.double()*(-.1) + dN.double().sqrt()*.15*torch.randn((n, p), dtype=torch.float64, device='cuda', generator=g)
+    t, x = timed(lambda: sd.merton_jumpdiff_process(
+        x0=1., mu=.05, sigma=.2, lam=2., a=-.1, b=.15, paths=p, steps=n + 1,
+        dw=sd.replay_source(dW), dj=sd.replay_source(dJ, dn=dN), output='device')((0., 1.)))
+    rec('C4 merton replay (dW + dJ + dN tables), terminal only', p, n, t, stored=2*p, read=3*p*n)
+    del x, dW, dJ, dN
     # summaries of a resident slab along the timeline (path-dependent payoffs)
     p, n = int(1_000_000*a.scale), 500
     proc = sd.ornstein_uhlenbeck_process(x0=.1, theta=.2, k=1., sigma=.3, paths=p, seed=8,
