@@ -1398,7 +1398,8 @@ extern "C" int sdeb_jit_compile(const char* source, const char* model_type, int6
     for (int k = 0; k < 10; ++k) jm.ghave[k] = false;
     std::vector<char> cubin;
     std::string plog;
-    int rc = nvrtc_cubin(jm.source, jm.name, {"-DSDEB_JIT_NO_GENERAL"}, cubin, plog);
+    // (this stage holds the lean entry only: contracted arithmetic, SDEB_CONTRACT)
+    int rc = nvrtc_cubin(jm.source, jm.name, {"-DSDEB_JIT_NO_GENERAL", "-DSDEB_CONTRACT=1"}, cubin, plog);
     if (log && log_bytes > 0) { strncpy(log, plog.c_str(), (size_t)log_bytes - 1); log[log_bytes - 1] = 0; }
     if (rc) return rc;
     CUDA_TRY(cudaLibraryLoadData(&jm.lib, cubin.data(), NULL, NULL, 0, NULL, NULL, 0));
