@@ -691,66 +691,164 @@ __device__ __forceinline__ double row_value(const double* lo, const double* hi, 
     return y;
 }
 
-enum { EVAL_CDF = 0, EVAL_CHF = 1, EVAL_QCHUNK = 8 };
+enum { EVAL_QCHUNK = 8, CDF_MAX_Q = 2048 };
 
-template <int MODE>
+// One row, possibly interpolated between two stored rows, streamed with 16-byte
+// loads (scalar accesses when a row is not 16-byte aligned): f(y) once per path.
+template <class F>
+__device__ __forceinline__ void stream_interp(const double* __restrict__ lo,
+                                              const double* __restrict__ hi, double w_lo,
+                                              double w_hi, int interp, int64_t n, F&& f) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const bool vec = ((((uintptr_t)lo) | (interp ? (uintptr_t)hi : 0)) & 15) == 0;
+    if (vec) {
+        const int64_t nvec = n >> 1;
+        const double2* __restrict__ lv = (const double2*)lo;
+        const double2* __restrict__ hv = (const double2*)hi;
+        int64_t i = tid;
+        for (; i + stride < nvec; i += 2 * stride) {
+            double2 a = __ldcs(lv + i), b = __ldcs(lv + i + stride);
+            if (interp) {
+                const double2 c = __ldcs(hv + i), d = __ldcs(hv + i + stride);
+                a.x = __dadd_rn(__dmul_rn(w_hi, c.x), __dmul_rn(w_lo, a.x));
+                a.y = __dadd_rn(__dmul_rn(w_hi, c.y), __dmul_rn(w_lo, a.y));
+                b.x = __dadd_rn(__dmul_rn(w_hi, d.x), __dmul_rn(w_lo, b.x));
+                b.y = __dadd_rn(__dmul_rn(w_hi, d.y), __dmul_rn(w_lo, b.y));
+            }
+            f(a.x); f(a.y); f(b.x); f(b.y);
+        }
+        for (; i < nvec; i += stride) {
+            double2 a = __ldcs(lv + i);
+            if (interp) {
+                const double2 c = __ldcs(hv + i);
+                a.x = __dadd_rn(__dmul_rn(w_hi, c.x), __dmul_rn(w_lo, a.x));
+                a.y = __dadd_rn(__dmul_rn(w_hi, c.y), __dmul_rn(w_lo, a.y));
+            }
+            f(a.x); f(a.y);
+        }
+        if (tid == 0 && (n & 1)) f(row_value(lo, hi, n - 1, w_lo, w_hi, 0.0, interp));
+    } else {
+        for (int64_t i = tid; i < n; i += stride) f(row_value(lo, hi, i, w_lo, w_hi, 0.0, interp));
+    }
+}
+
+// process.cdf: counts[j] += #{paths : y <= q[j]} for ANY number and order of
+// thresholds in ONE pass over the row.  Each block rank-sorts the thresholds in
+// shared memory; a value's bucket is the first sorted threshold >= y (binary
+// search, log2(nq) steps instead of nq comparisons), counted in warp-private
+// shared counters; a prefix sum over the buckets gives the counts (integers:
+// exact, order-independent).  NaN values fall in no bucket, NaN thresholds count 0.
 __global__ void __launch_bounds__(256)
-path_eval_kernel(const double* lo, const double* hi, double t_lo, double dt_knots, double t,
-                 /* t_lo, dt_knots carry w_lo, w_hi */
-                 int interp, int64_t n_paths, const double* q, int nq,
-                 unsigned long long* counts, double* partials) {
+path_cdf_kernel(const double* lo, const double* hi, double w_lo, double w_hi, int interp,
+                int64_t n_paths, const double* q, int nq, unsigned long long* counts) {
+    extern __shared__ double sh[];
+    double* s_q = sh;                                   // sorted thresholds (NaNs last)
+    int* s_perm = (int*)(sh + nq);                      // sorted position -> caller's index
+    unsigned int* s_cnt = (unsigned int*)(s_perm + nq); // 8 warps x (nq + 1) buckets
+    const int cstride = nq + 1;
+    for (int j = threadIdx.x; j < nq; j += blockDim.x) {
+        const double qj = q[j];
+        const bool nanj = qj != qj;
+        int r = 0;
+        for (int k = 0; k < nq; ++k) {
+            const double qk = q[k];
+            const bool nank = qk != qk;
+            r += nanj ? (!nank || k < j) : (!nank && (qk < qj || (qk == qj && k < j)));
+        }
+        s_q[r] = qj; s_perm[r] = j;
+    }
+    for (int i = threadIdx.x; i < 8 * cstride; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    unsigned int* my = s_cnt + (threadIdx.x >> 5) * cstride;
+    stream_interp(lo, hi, w_lo, w_hi, interp, n_paths, [&](double y) {
+        int a = 0, b = nq;                              // first index with s_q[idx] >= y
+        while (a < b) { const int m = (a + b) >> 1; if (s_q[m] >= y) b = m; else a = m + 1; }
+        // (a NaN y compares false everywhere: a ends at nq, the "no threshold" bucket)
+        atomicAdd(&my[a], 1u);
+    });
+    __syncthreads();
+    for (int i = threadIdx.x; i <= nq; i += blockDim.x) {
+        unsigned int t = 0;
+        for (int w = 0; w < 8; ++w) t += s_cnt[w * cstride + i];
+        s_cnt[i] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int j = 0; j < nq; ++j) {
+            run += s_cnt[j];
+            if (run && s_q[j] == s_q[j]) atomicAdd(&counts[s_perm[j]], run);
+        }
+    }
+}
+
+// process.chf: sums of cos(u_j y), sin(u_j y) over the paths.  When the
+// frequencies form an arithmetic progression (the usual grid), each chunk of 8
+// is evaluated exactly at its first frequency and ROTATED by (cos, sin)(du y)
+// for the next seven (7 rotations: ~1e-15) -- 1 + nq/8 sincos per path instead of nq.
+__global__ void __launch_bounds__(256)
+path_chf_kernel(const double* lo, const double* hi, double w_lo, double w_hi, int interp,
+                int64_t n_paths, const double* q, int nq, double* partials) {
     __shared__ double s_red[8][2 * EVAL_QCHUNK];
+    __shared__ int s_grid;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        int ok = nq >= 3;
+        const double u0 = q[0], du = nq > 1 ? q[1] - q[0] : 0.0;
+        double big = 0.0;
+        for (int j = 0; j < nq; ++j) big = fmax(big, fabs(q[j]));
+        for (int j = 2; j < nq && ok; ++j) ok = fabs(q[j] - (u0 + j * du)) <= 8.9e-16 * big;
+        s_grid = ok;
+    }
+    __syncthreads();
+    const bool grid = s_grid != 0;
+    const double du = nq > 1 ? q[1] - q[0] : 0.0;
     for (int q0 = 0; q0 < nq; q0 += EVAL_QCHUNK) {
         double qv[EVAL_QCHUNK];
         double a0[EVAL_QCHUNK], a1[EVAL_QCHUNK];
-        unsigned int cnt[EVAL_QCHUNK];
 #pragma unroll
         for (int j = 0; j < EVAL_QCHUNK; ++j) {
             qv[j] = (q0 + j < nq) ? q[q0 + j] : 0.0;
-            a0[j] = a1[j] = 0.0; cnt[j] = 0;
+            a0[j] = a1[j] = 0.0;
         }
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_paths;
-             i += (int64_t)gridDim.x * blockDim.x) {
-            double y = row_value(lo, hi, i, t_lo, dt_knots, t, interp);
+        stream_interp(lo, hi, w_lo, w_hi, interp, n_paths, [&](double y) {
+            if (grid) {
+                double sn, cs, sd, cd;
+                sincos(qv[0] * y, &sn, &cs);
+                sincos(du * y, &sd, &cd);
 #pragma unroll
-            for (int j = 0; j < EVAL_QCHUNK; ++j) {
-                if (MODE == EVAL_CDF) {
-                    cnt[j] += (y <= qv[j]) ? 1u : 0u;
-                } else {
+                for (int j = 0; j < EVAL_QCHUNK; ++j) {
+                    a0[j] += cs; a1[j] += sn;
+                    const double c2 = cs * cd - sn * sd;
+                    sn = sn * cd + cs * sd; cs = c2;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < EVAL_QCHUNK; ++j) {
                     double sn, cs;
                     sincos(qv[j] * y, &sn, &cs);
                     a0[j] += cs; a1[j] += sn;
                 }
             }
+        });
+#pragma unroll
+        for (int j = 0; j < EVAL_QCHUNK; ++j) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                a0[j] += __shfl_down_sync(0xffffffffu, a0[j], off);
+                a1[j] += __shfl_down_sync(0xffffffffu, a1[j], off);
+            }
+            if (lane == 0) { s_red[warp][2*j] = a0[j]; s_red[warp][2*j + 1] = a1[j]; }
         }
-        if (MODE == EVAL_CDF) {
-#pragma unroll
-            for (int j = 0; j < EVAL_QCHUNK; ++j) {
-                unsigned int c = cnt[j];
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
-                if (lane == 0 && q0 + j < nq && c) atomicAdd(&counts[q0 + j], (unsigned long long)c);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < EVAL_QCHUNK; ++j) {
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    a0[j] += __shfl_down_sync(0xffffffffu, a0[j], off);
-                    a1[j] += __shfl_down_sync(0xffffffffu, a1[j], off);
-                }
-                if (lane == 0) { s_red[warp][2*j] = a0[j]; s_red[warp][2*j + 1] = a1[j]; }
-            }
-            __syncthreads();
-            if (threadIdx.x < 2 * EVAL_QCHUNK && q0 + (int)threadIdx.x / 2 < nq) {
-                double acc = 0.0;
-                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) acc += s_red[w][threadIdx.x];
-                // [block][nq][2]
-                partials[((int64_t)blockIdx.x * nq + q0) * 2 + threadIdx.x] = acc;
-            }
-            __syncthreads();
+        __syncthreads();
+        if (threadIdx.x < 2 * EVAL_QCHUNK && q0 + (int)threadIdx.x / 2 < nq) {
+            double acc = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) acc += s_red[w][threadIdx.x];
+            // [block][nq][2]
+            partials[((int64_t)blockIdx.x * nq + q0) * 2 + threadIdx.x] = acc;
         }
+        __syncthreads();
     }
 }
 
@@ -780,12 +878,19 @@ extern "C" int sdeb_path_cdf(const double* y_lo, const double* y_hi, double w_lo
                              int64_t nq, int64_t* counts, void* stream_) {
     if (!y_lo || (interp && !y_hi) || !q || !counts || n_paths < 1 || nq < 1)
         return fail(SDEB_EINVAL, "sdeb_path_cdf: bad arguments");
-    int64_t need = (n_paths + 255) / 256;
-    int blocks = (int)(need < kEvalBlocks ? need : kEvalBlocks);
-    path_eval_kernel<EVAL_CDF><<<blocks, 256, 0, (cudaStream_t)stream_>>>(
-        y_lo, y_hi, w_lo, w_hi, 0.0, (int)interp, n_paths, q, (int)nq,
-        (unsigned long long*)counts, NULL);
-    CUDA_TRY(cudaGetLastError());
+    int64_t need = (n_paths + 1023) / 1024;
+    int blocks = (int)(need < 1184 ? need : 1184);
+    for (int64_t q0 = 0; q0 < nq; q0 += CDF_MAX_Q) {       // one pass per 2048 thresholds
+        const int m = (int)(nq - q0 < CDF_MAX_Q ? nq - q0 : CDF_MAX_Q);
+        size_t smem = (size_t)m * 12 + (size_t)8 * (m + 1) * 4;
+        if (smem > 48 * 1024)
+            CUDA_TRY(cudaFuncSetAttribute(path_cdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+        path_cdf_kernel<<<blocks, 256, smem, (cudaStream_t)stream_>>>(
+            y_lo, y_hi, w_lo, w_hi, (int)interp, n_paths, q + q0, m,
+            (unsigned long long*)counts + q0);
+        CUDA_TRY(cudaGetLastError());
+    }
     return SDEB_OK;
 }
 
@@ -798,11 +903,10 @@ extern "C" int sdeb_path_chf(const double* y_lo, const double* y_hi, double w_lo
     if (!workspace || workspace_bytes < sdeb_path_eval_workspace(nq))
         return fail(SDEB_EINVAL, "sdeb_path_chf: workspace too small");
     cudaStream_t stream = (cudaStream_t)stream_;
-    int64_t need = (n_paths + 255) / 256;
+    int64_t need = (n_paths + 1023) / 1024;
     int blocks = (int)(need < kEvalBlocks ? need : kEvalBlocks);
-    path_eval_kernel<EVAL_CHF><<<blocks, 256, 0, stream>>>(
-        y_lo, y_hi, w_lo, w_hi, 0.0, (int)interp, n_paths, u, (int)nq, NULL,
-        (double*)workspace);
+    path_chf_kernel<<<blocks, 256, 0, stream>>>(y_lo, y_hi, w_lo, w_hi, (int)interp, n_paths, u,
+                                                (int)nq, (double*)workspace);
     CUDA_TRY(cudaGetLastError());
     int64_t len = nq * 2;
     fold_sum_kernel<<<(unsigned)((len + 127) / 128), 128, 0, stream>>>(
