@@ -207,7 +207,8 @@ int sdeb_moments(const double* x, int64_t n_rows, int64_t n_paths, int64_t pitch
  *  sdeb_mc_update : ONE pass giving the power sums S1..S4 of (x - centre)
  *      (stats[row][0..3], 2940-2946) AND the histogram (counts/outside are
  *      ACCUMULATED, 3010-3013), every row with its own edges[row][nbins+1].
- *      centre == NULL: centre = range_stats[row][0] / n.
+ *      centre == NULL: centre = range_stats[row][0] / n (written to centre_out, if given,
+ *      so that later updates cumulate about the same constant).
  *      edges_mode SDEB_MC_EDGES_GIVEN: edges are read; _MINMAX / _RANGE: edges are
  *      BUILT on the device exactly as numpy.linspace(lo, hi, nbins + 1) does
  *      (step = (hi - lo)/nbins, e_i = fl(fl(i*step) + lo), e_nbins = hi; lo == hi
@@ -223,6 +224,7 @@ int sdeb_mc_range(const double* x, int64_t n_rows, int64_t n, int64_t pitch, dou
                   void* workspace, int64_t workspace_bytes, void* stream);
 int sdeb_mc_update(const double* x, int64_t n_rows, int64_t n, int64_t pitch,
                    const double* centre /* [n_rows] device or NULL */,
+                   double* centre_out /* [n_rows] device or NULL: the centre used */,
                    const double* range_stats /* [n_rows][SDEB_NSTAT] device or NULL */,
                    double range_lo, double range_hi, int64_t edges_mode,
                    double* edges /* [n_rows][nbins+1] device */, int64_t nbins,

@@ -185,7 +185,7 @@ def mc_range(x2d, n, out=None):
     return stats
 
 
-def mc_update(x2d, n, *, centre=None, range_stats=None, lo=0., hi=0.,
+def mc_update(x2d, n, *, centre=None, centre_out=None, range_stats=None, lo=0., hi=0.,
               edges_mode=_lib.MC_EDGES_GIVEN, edges=None, nbins=0, uniform=True,
               counts=None, outside=None, out=None):
     """Fused moments + histogram pass (sdeb_mc_update) over the rows of x2d;
@@ -197,7 +197,8 @@ def mc_update(x2d, n, *, centre=None, range_stats=None, lo=0., hi=0.,
     ws, ws_bytes = _workspace(rows, dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib.sdeb_mc_update(
-            ptr(x2d), rows, n, pitch, ptr(centre), ptr(range_stats), float(lo), float(hi),
+            ptr(x2d), rows, n, pitch, ptr(centre), ptr(centre_out), ptr(range_stats),
+            float(lo), float(hi),
             int(edges_mode), ptr(edges), int(nbins), int(bool(uniform)), ptr(stats),
             ptr(counts), ptr(outside), ptr(ws), ws_bytes, stream_ptr(dev)))
     return stats

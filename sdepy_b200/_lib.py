@@ -71,7 +71,7 @@ def _load():
     lib.sdeb_moments.argtypes = [ptr, i64, i64, i64, ptr, ptr, ptr, i64, ptr]
     lib.sdeb_histogram.argtypes = [ptr, i64, ptr, i64, i64, ptr, ptr, ptr]
     lib.sdeb_mc_range.argtypes = [ptr, i64, i64, i64, ptr, ptr, i64, ptr]
-    lib.sdeb_mc_update.argtypes = [ptr, i64, i64, i64, ptr, ptr, f64, f64, i64, ptr, i64, i64,
+    lib.sdeb_mc_update.argtypes = [ptr, i64, i64, i64, ptr, ptr, ptr, f64, f64, i64, ptr, i64, i64,
                                    ptr, ptr, ptr, ptr, i64, ptr]
     lib.sdeb_path_eval_workspace.restype = i64
     lib.sdeb_path_eval_workspace.argtypes = [i64]

@@ -480,6 +480,7 @@ enum { MC_EDGES_GIVEN = 0, MC_EDGES_MINMAX = 1, MC_EDGES_RANGE = 2 };
 
 __global__ void __launch_bounds__(256)
 mc_update_kernel(const double* x, int64_t n, int64_t pitch, const double* centre,
+                 double* centre_out,
                  const double* range_stats, double range_lo, double range_hi, int edges_mode,
                  double* edges, int nbins, int uniform, int copies,
                  double* partials, unsigned long long* counts, unsigned long long* outside) {
@@ -491,6 +492,7 @@ mc_update_kernel(const double* x, int64_t n, int64_t pitch, const double* centre
     const int cstride = nbins + 1;                              // last slot: outside
     const double* xr = x + (int64_t)row * pitch;
     const double c = centre ? centre[row] : __ddiv_rn(range_stats[row * NSTAT], (double)n);
+    if (centre_out && blockIdx.x == 0 && threadIdx.x == 0) centre_out[row] = c;
     if (threadIdx.x == 0) s_exact = uniform;
     __syncthreads();
     if (nbins > 0) {
@@ -604,7 +606,7 @@ mc_update_kernel(const double* x, int64_t n, int64_t pitch, const double* centre
 }
 
 extern "C" int sdeb_mc_update(const double* x, int64_t n_rows, int64_t n, int64_t pitch,
-                              const double* centre, const double* range_stats,
+                              const double* centre, double* centre_out, const double* range_stats,
                               double range_lo, double range_hi, int64_t edges_mode,
                               double* edges, int64_t nbins, int64_t uniform_edges,
                               double* stats, int64_t* counts, int64_t* outside,
@@ -634,7 +636,7 @@ extern "C" int sdeb_mc_update(const double* x, int64_t n_rows, int64_t n, int64_
         CUDA_TRY(cudaFuncSetAttribute(mc_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     mc_update_kernel<<<dim3(blocks, (unsigned)n_rows), 256, smem, stream>>>(
-        x, n, pitch, centre, range_stats, range_lo, range_hi, (int)edges_mode, edges, (int)nbins,
+        x, n, pitch, centre, centre_out, range_stats, range_lo, range_hi, (int)edges_mode, edges, (int)nbins,
         (int)uniform_edges, copies, (double*)workspace, (unsigned long long*)counts,
         (unsigned long long*)outside);
     CUDA_TRY(cudaGetLastError());

@@ -1645,13 +1645,7 @@ class montecarlo:
                             raise ValueError('autodetected range of [{}, {}] is not finite'
                                              .format(lo_i, hi_i))
                 center = (rs[:, 0]/m).reshape(vshape)
-                self._groups = groups
-                at = 0
-                for g in groups:        # later updates cumulate about the same centre
-                    k = g['r1'] - g['r0']
-                    g['centre'].copy_(torch.from_numpy(center.reshape(-1)[at:at + k]),
-                                      non_blocking=True)
-                    at += k
+                self._groups = groups       # (the kernel left the centre it used in g['centre'])
                 if nb:
                     self._edges, self._uniform = [], [True]*nrow
                     for h in host:
@@ -1756,6 +1750,7 @@ class montecarlo:
             r0, r1 = g['r0'], g['r1']
             _cuda.mc_update(
                 rows[r0:r1], m, centre=g['centre'] if centre == 'own' else None,
+                centre_out=None if centre == 'own' else g['centre'],
                 range_stats=g['range'] if from_range else None,
                 lo=lo, hi=hi, edges_mode=mode, edges=g['edges'], nbins=g['nbins'],
                 uniform=g['uniform'], counts=g['counts'], outside=g['outside'],
