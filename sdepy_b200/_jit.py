@@ -462,7 +462,7 @@ JIT_ENTRIES = [
     'sdeb_jit_entry_lean(const sdeb::KArgs a) {',
     '    if (sdeb::UserModel::NPC + (sdeb::UserModel::NDW > 1 ? sdeb::UserModel::NDW *',
     '        (sdeb::UserModel::NDW + 1) / 2 : 0) <= sdeb::MAX_CBANK_PARAMS)',
-    '        sdeb::integrate_body<sdeb::UserModel, true,\n            sdeb::UserModel::JUMPS ? 1 : SDEB_LEAN_PPT>(a);',
+    '        sdeb::integrate_body<sdeb::UserModel, true,\n            sdeb::UserModel::JUMPS ? SDEB_LEAN_JUMP_PPT : SDEB_LEAN_PPT>(a);',
     '}',
     '#endif',
     '#ifdef SDEB_JIT_STREAM',
