@@ -171,3 +171,85 @@ def test_path_dependent_payoffs_on_the_device():
     lb = p.tmax().x[0] - p.x[-1]
     assert np.array_equal(a.cpu().numpy(), asian)
     assert np.array_equal(lb.cpu().numpy(), lookback)
+
+
+@pytest.mark.parametrize('lo,width,nbins', [(0., 1., 7), (-3., 6., 100), (1e6, 1e-3, 64),
+                                            (-1e-300, 2e-300, 10), (123.456, 7.89e5, 4000)])
+def test_fused_histogram_next_to_the_bin_boundaries(lo, width, nbins):
+    """mc_update_kernel decides the bin arithmetically unless the value lies
+    within a rigorous margin of a boundary (then it compares with the exact
+    edges): values ON every edge, one ulp below and above it, and random ones,
+    at ranges whose edges are coarse or fine in ulps -- counts must equal
+    numpy.histogram's for range=None (edges from the sample's min / max) and for
+    an explicit range, one-shot and cumulated."""
+    m = sd()
+    rng = np.random.default_rng(int(nbins))
+    hi = lo + width
+    e = np.linspace(lo, hi, nbins + 1)
+    near = np.concatenate((e, np.nextafter(e, -np.inf), np.nextafter(e, np.inf)))
+    x = np.concatenate((near, rng.uniform(lo, hi, 200_003), [lo, hi]))
+    x = x[(x >= lo) & (x <= hi)]
+    rng.shuffle(x)
+    a = m.montecarlo(x, bins=nbins)
+    c, edges = np.histogram(x, bins=nbins)
+    assert np.array_equal(a.histogram()[1], edges)
+    assert np.array_equal(a.histogram()[0], c) and a.outpaths == 0
+    # explicit range narrower than the data, then a second sample cumulated
+    r = (lo + .25*width, lo + .75*width)
+    b = m.montecarlo(x, bins=nbins, range=r)
+    c1, e1 = np.histogram(x, bins=nbins, range=r)
+    assert np.array_equal(b.histogram()[1], e1) and np.array_equal(b.histogram()[0], c1)
+    assert b.outpaths == x.size - c1.sum()
+    y = rng.uniform(lo, hi, 50_001)
+    b.update(y)
+    c2, _ = np.histogram(y, bins=e1)
+    assert np.array_equal(b.histogram()[0], c1 + c2)
+    assert b.outpaths == x.size + y.size - (c1 + c2).sum()
+    assert np.allclose(b.mean(), np.concatenate((x, y)).mean(), rtol=1e-12)
+
+
+def test_fused_histogram_degenerate_samples():
+    m = sd()
+    a = m.montecarlo(np.full(1000, 2.5), bins=10)              # min == max: widened by 1/2
+    c, e = np.histogram(np.full(1000, 2.5), bins=10)
+    assert np.array_equal(a.histogram()[0], c) and np.array_equal(a.histogram()[1], e)
+    x = np.arange(10.)
+    x[3] = np.nan
+    with pytest.raises(ValueError):
+        m.montecarlo(x, bins=5)                                  # numpy: range not finite
+    b = m.montecarlo(x, bins=5, range=(0., 9.))                 # NaN counted outside
+    assert b.histogram()[0].sum() == 9 and b.outpaths == 1
+    one = m.montecarlo(np.array([1.5]), bins=3)
+    assert one.histogram()[0].sum() == 1 and one.paths == 1
+
+
+def test_cdf_any_order_and_number_of_thresholds():
+    """path_cdf_kernel rank-sorts the thresholds per block: unsorted, repeated,
+    infinite and NaN thresholds, and more than 2048 of them (two passes)."""
+    import torch
+    m = sd()
+    rng = np.random.default_rng(8)
+    x = rng.normal(size=(1, 300_001))
+    x[0, :50] = np.nan
+    dp = m.device_process(np.zeros(1), torch.from_numpy(x).cuda())
+    q = np.array([.3, -1., .3, np.inf, -np.inf, np.nan, 2.5, 0., -1.])
+    got = dp.cdf(q)
+    want = np.array([(x[0] <= v).mean() for v in q])
+    assert np.array_equal(got.reshape(-1), want)
+    q = rng.normal(size=5000)
+    got = dp.cdf(q).reshape(-1)
+    srt = np.sort(x[0][~np.isnan(x[0])])
+    want = np.searchsorted(srt, q, side='right')/x.shape[1]
+    assert np.array_equal(got, want)
+    # interpolated row, odd path count (scalar tail of the 16-byte loads)
+    x2 = rng.normal(size=(2, 100_001))
+    dp2 = m.device_process(np.array([0., 1.]), torch.from_numpy(x2).cuda())
+    qq = np.linspace(-2, 2, 33)
+    y = .25*x2[1] + .75*x2[0]
+    assert np.array_equal(dp2.cdf(.25, qq).reshape(-1), np.array([(y <= v).mean() for v in qq]))
+    u = np.linspace(-3., 3., 21)
+    assert np.allclose(dp2.chf(.25, u).reshape(-1), np.exp(1j*u[:, None]*y).mean(axis=-1),
+                       rtol=1e-12, atol=1e-15)
+    u2 = np.array([.1, -2., .7, 5., .1])                          # not a grid: plain sincos
+    assert np.allclose(dp2.chf(.25, u2).reshape(-1), np.exp(1j*u2[:, None]*y).mean(axis=-1),
+                       rtol=1e-12, atol=1e-15)
