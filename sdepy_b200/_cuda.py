@@ -39,6 +39,10 @@ def to_device(a, dev, dtype=None):
     return t.to(dev, non_blocking=True)
 
 
+_TORCH_DTYPE = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
+                np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64}
+
+
 def upload_packed(arrays, dev):
     """Several small host arrays -> device tensors through ONE page-locked
     staging buffer and ONE async H2D copy (the per-launch tables: steps, store
@@ -56,7 +60,7 @@ def upload_packed(arrays, dev):
     d = host.to(dev, non_blocking=True)
     out = []
     for a, o in zip(arrays, offs):
-        t = d[o:o + a.nbytes].view(getattr(torch, a.dtype.name)).reshape(a.shape)
+        t = d[o:o + a.nbytes].view(_TORCH_DTYPE[a.dtype]).reshape(a.shape)   # (dtype.name is slow)
         t._sdeb_staging = host           # keep the pinned block until the copy has run
         out.append(t)
     return out
