@@ -101,10 +101,11 @@ typedef struct sdeb_problem {
                                  split into Poisson(lam|dt|/m) terms); jump sizes:
                                  stream 0x200 + j.  Results depend on (seed, global
                                  path, group) only -- not on the sharding, the grid or
-                                 the launch geometry; the lean kernel (sdeb_plan_t.kernel
-                                 == 1: Philox, one time-invariant record) contracts its
-                                 step arithmetic into FMAs and agrees with the other
-                                 two to rounding level (~1e-14 over a few hundred steps) */
+                                 the launch geometry or which kernel (sdeb_plan_t.kernel)
+                                 runs.  Rounding: replayed increments, and Philox runs
+                                 with dW_dump set, round every product and sum of the
+                                 step like NumPy; plain Philox runs contract the preset
+                                 steps into FMAs (~1e-14 apart over a few hundred steps) */
     const double* steps;      /* [n_steps][2]: dt = t[n+1]-t[n] (integration.py:714),
                                  sqrt|dt| (infrastructure.py:1558-1559)         */
     const int32_t* store_row; /* [n_steps]: row storing the state after step n
