@@ -1549,6 +1549,10 @@ static int jit_general_kernel(int64_t handle, int variant, const void** fn) {
             entry = "sdeb_jit_entry_stream";
         }
         defs.push_back(def);
+        // the rounding rule (sde_engine.cuh:clamp_tiny): a variant that serves plain
+        // Philox runs -- general sweeps 0, 1, stream variants 0, 1 -- is a translation
+        // unit of its own and compiles the traced step with plain, contractible operators
+        if (variant < 2 || variant == 6 || variant == 7) defs.push_back("-DSDEB_CONTRACT=1");
         std::vector<char> cubin;
         std::string plog;
         int rc = nvrtc_cubin(jm.source, jm.name, defs, cubin, plog);
