@@ -277,11 +277,13 @@ class path_stats:
 
     def skew(self):
         m1, m2, m3 = self._m(1), self._m(2), self._m(3)
-        return self._proc((m3 - 3*m1*m2 + 2*m1**3)/(m2 - m1*m1)**1.5)
+        with np.errstate(invalid='ignore', divide='ignore'):     # zero variance at t0: nan
+            return self._proc((m3 - 3*m1*m2 + 2*m1**3)/(m2 - m1*m1)**1.5)
 
     def kurtosis(self):
         m1, m2, m3, m4 = (self._m(k) for k in (1, 2, 3, 4))
-        return self._proc((m4 - 4*m1*m3 + 6*m1*m1*m2 - 3*m1**4)/(m2 - m1*m1)**2)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            return self._proc((m4 - 4*m1*m3 + 6*m1*m1*m2 - 3*m1**4)/(m2 - m1*m1)**2)
 
     def pmin(self):
         return self._proc(self.sums[..., 4])
