@@ -233,9 +233,15 @@ def euler_replay(model, params, x0, grid, where, dW, dJ=None, dN=None,
 
 
 def generic_replay(sde, params, x0, grid, where, dW, log=False,
-                   scheme='euler', diffusion_dx=None):
+                   scheme='euler', diffusion_dx=None, dN=None, dJ=None,
+                   let=None, info_next=None):
     """Replay driver for a user ``sde(t, x, **params) -> {'dt':.., 'dw':..}``
-    function (the ``integrate`` decorator path, integration.py:1843-1955)."""
+    function (the ``integrate`` decorator path, integration.py:1843-1955);
+    optionally with 'dn' / 'dj' terms fed from recorded increments, a user
+    ``let`` (the value stored at output points, SDE.store -> let, 1175-1186,
+    1501-1528) and a user ``info_next(last_x, new_x) -> {key: increment}``
+    accumulated after every step (SDE.next -> info_next, 1169-1173).  Returns
+    ``xx``, or ``(xx, info)`` when ``info_next`` is given."""
     grid = np.asarray(grid, dtype=float)
     out_of = {int(j): i for i, j in enumerate(where)}
     dW = np.asarray(dW)
@@ -243,24 +249,36 @@ def generic_replay(sde, params, x0, grid, where, dW, log=False,
     x[...] = np.asarray(x0)
     if log:
         x = np.log(x)
-    rows = [x.copy()] if 0 in out_of else []
+    store = (lambda z: z.copy()) if let is None else let
+    rows = [store(x)] if 0 in out_of else []
+    info = {}
     for n in range(grid.size - 1):
         s, ds = grid[n], grid[n+1] - grid[n]
         p = _at(params, s)
         A = sde(s, x, **p)
         terms = [(A[k], k) for k in A.keys()]
         dz = {'dt': ds, 'dw': dW[n]}
+        if dN is not None:
+            dz['dn'] = dN[n]
+        if dJ is not None:
+            dz['dj'] = dJ[n]
+        last = x
         if scheme == 'milstein':
             x = milstein(x, terms, dz, diffusion_dx(s, x, **p))
         else:
             x = _euler_sum(x, terms, dz)
+        if info_next is not None:
+            for k, v in info_next(last, x).items():
+                info[k] = info.get(k, 0) + v
         if n + 1 in out_of:
-            rows.append(x.copy())
+            rows.append(store(x))
     xx = np.stack(rows)
-    return np.exp(xx) if log else xx
+    xx = np.exp(xx) if log else xx
+    return xx if info_next is None else (xx, info)
 
 
-def system_replay(sde, q, params, x0s, grid, where, dW, addaxis, dN=None, dJ=None):
+def system_replay(sde, q, params, x0s, grid, where, dW, addaxis, dN=None, dJ=None,
+                  let=None, info_next=None):
     """Replay driver for a user system ``sde(t, x1..xq, **params) -> (dict,)*q``
     (``SDEs``, integration.py:1584-1835).  The q equations are stacked along a
     new axis -2 (``addaxis``) or along the last axis of vshape, equation k
@@ -283,6 +301,7 @@ def system_replay(sde, q, params, x0s, grid, where, dW, addaxis, dN=None, dJ=Non
         tuple(np.broadcast_to(z, vshape + (paths,))[idx] for z in zs), axis=-2)
     X = pack(tuple(np.asarray(z, dtype=float) for z in x0s))
     rows = [X.copy()] if 0 in out_of else []
+    info = {}
     for n in range(grid.size - 1):
         s, ds = grid[n], grid[n+1] - grid[n]
         As = sde(s, *unpack(X), **_at(params, s))
@@ -295,10 +314,19 @@ def system_replay(sde, q, params, x0s, grid, where, dW, addaxis, dN=None, dJ=Non
             dz['dn'] = dN[n]
         if dJ is not None:
             dz['dj'] = dJ[n]
+        last = X
         X = _euler_sum(X, terms, dz)
+        if info_next is not None:
+            for k, v in info_next(unpack(last), unpack(X)).items():
+                info[k] = info.get(k, 0) + v
         if n + 1 in out_of:
             rows.append(X.copy())
-    return tuple(np.stack([unpack(r)[k] for r in rows]) for k in range(q))
+    if let is not None:
+        # a user let() over the unpacked equations (one stored array)
+        xx = np.stack([let(*unpack(r)) for r in rows])
+        return xx if info_next is None else (xx, info)
+    out = tuple(np.stack([unpack(r)[k] for r in rows]) for k in range(q))
+    return out if info_next is None else (out, info)
 
 
 def milstein(x, terms, dz, b_dx):

@@ -235,3 +235,30 @@ def test_milstein_pinned_to_the_reference_machinery_with_a_plugged_in_scheme():
         got = orc.generic_replay(f, par, x0, grid, where, dW, scheme='milstein',
                                  diffusion_dx=b_dx)
         assert np.array_equal(got, want), name
+
+
+def test_user_hooks_and_two_jump_terms_bit_exact():
+    """The oracle's replay drivers with a user let / info_next and with both a
+    'dn' and a 'dj' term, against the fixtures the reference produced for them
+    (tests/golden/make_user_hooks.py, make_two_jump_terms.py)."""
+    from tests.cases import two_jump_terms
+    g = golden('replay_user_hooks')
+    where = [int(np.searchsorted(g['a_grid'], t)) for t in g['a_tt']]
+    xx, info = orc.generic_replay(
+        lambda t, x, k=1., s=.4: {'dt': -k*x, 'dw': s}, dict(k=g['a_k']), .3, g['a_grid'], where,
+        g['a_dW'], let=lambda x: x*x + 1.,
+        info_next=lambda last, new: {'neg': (last < 0)*1, 'big': (new > .25)*1})
+    assert np.array_equal(xx, g['a_out'])
+    assert np.array_equal(info['neg'], g['a_neg']) and np.array_equal(info['big'], g['a_big'])
+    assert int(info['neg'].sum()) == int(g['a_total_neg'])
+    where = [int(np.searchsorted(g['b_grid'], t)) for t in g['b_tt']]
+    xx, info = orc.system_replay(
+        lambda t, x, y, a=.5: ({'dt': -a*x, 'dw': y}, {'dt': a*(1 - y), 'dw': .2*y}), 2, {},
+        (1., .8), g['b_grid'], where, g['b_dW'], False, let=lambda x, y: x*y,
+        info_next=lambda last, new: {'ylow': (last[1] < .9)*1})
+    assert np.array_equal(xx, g['b_out']) and np.array_equal(info['ylow'], g['b_ylow'])
+    g = golden('replay_two_jump_terms')
+    where = [int(np.searchsorted(g['grid'], t)) for t in g['tt']]
+    xx = orc.generic_replay(two_jump_terms, dict(a=g['p_a']), 1., g['grid'], where, g['dW'],
+                            dN=g['dN'], dJ=g['dJ'])
+    assert np.array_equal(xx, g['out'])
