@@ -95,13 +95,16 @@ static const int64_t kMaxStatsSmem = 96 * 1024;   // accumulators kept in smem u
 static int64_t smem_bytes(const ModelInfo& mi, const sdeb_problem* p, bool stats_in_kernel) {
     int64_t nch = mi.ndw > 1 ? (int64_t)mi.ndw * (mi.ndw + 1) / 2 : 0;
     int64_t npt = mi.npc + nch;
-    // dynamic part only (generator tables first); the staged step block is static __shared__;
-    // parameter records are staged only when time-dependent and shared by the paths
+    // dynamic part only; the staged step block is static __shared__.  The generator
+    // tables start on the first TAB_ALIGN boundary of the dynamic window (reserve a
+    // whole TAB_ALIGN in front of them); parameter records (staged only when
+    // time-dependent and shared by the paths) and the warp scratch live inside that
+    // gap when they fit its first TAB_FRONT bytes (sde_engine.cuh:integrate_body)
     const bool staged = p->n_psteps > 1 && !p->params_per_path;
-    int64_t d = (int64_t)TAB_DOUBLES * SDEB_TAB_COPIES +
-                (staged ? (int64_t)STEP_CHUNK * npt : 0) + 8 * NSTAT * mi.nx;
-    if (stats_in_kernel) d += p->n_rows * p->n_groups * mi.nx * NSTAT;
-    int64_t bytes = d * 8;
+    int64_t small = ((staged ? (int64_t)STEP_CHUNK * npt : 0) + 8 * NSTAT * mi.nx) * 8;
+    int64_t bytes = TAB_ALIGN + (int64_t)TAB_DOUBLES * SDEB_TAB_COPIES * 8 +
+                    (small > TAB_FRONT ? small : 0);
+    if (stats_in_kernel) bytes += p->n_rows * p->n_groups * mi.nx * NSTAT * 8;
     if (p->noise == SDEB_NOISE_REPLAY)       // cp.async ring of the replay table
         bytes += (int64_t)replay_depth(mi.ndw) * mi.ndw * kThreads * 8;
     return bytes;
@@ -129,14 +132,11 @@ static int stream_variant(const sdeb_problem* p) {
 }
 static int64_t stream_smem_bytes(const ModelInfo& mi, const sdeb_problem* p) {
     int64_t nch = mi.ndw > 1 ? (int64_t)mi.ndw * (mi.ndw + 1) / 2 : 0;
-    int64_t d = 0;
-    if (p->noise != SDEB_NOISE_REPLAY) d += (int64_t)TAB_DOUBLES * SDEB_TAB_COPIES;
-    if (p->n_psteps > 1) d += (int64_t)STEP_CHUNK * ((mi.npc + nch + 1) & ~(int64_t)1);
-    if (p->noise == SDEB_NOISE_REPLAY) {
-        const int64_t ne = mi.ndw + (mi.jumps ? 2 * (int64_t)mi.jumps * mi.nw : 0);
-        d += (int64_t)stream_depth((int)ne) * ne * kThreads * 2;
-    }
-    return d * 8;
+    int64_t par = p->n_psteps > 1 ? (int64_t)STEP_CHUNK * ((mi.npc + nch + 1) & ~(int64_t)1) * 8 : 0;
+    if (p->noise != SDEB_NOISE_REPLAY)      // tables on a TAB_ALIGN boundary, records in the gap
+        return TAB_ALIGN + (int64_t)TAB_DOUBLES * SDEB_TAB_COPIES * 8 + (par > TAB_FRONT ? par : 0);
+    const int64_t ne = mi.ndw + (mi.jumps ? 2 * (int64_t)mi.jumps * mi.nw : 0);
+    return par + (int64_t)stream_depth((int)ne) * ne * kThreads * 2 * 8;
 }
 
 // the lean kernel serves the hot configuration: Philox draws, one
