@@ -125,6 +125,26 @@ def test_stream_backward_sweep_and_per_path_x0():
         assert torch.equal(xs.x[i0].cpu(), torch.from_numpy(x0))
 
 
+def test_stream_dense_and_sparse_step_blocks():
+    """Step blocks (64 steps) whose steps all store into consecutive rows take the
+    advancing-cursor loop, the others look each row up: both in one run, either order."""
+    m = sd()
+    paths = 1030
+    dense, sparse = np.linspace(0., 1., 65), np.linspace(1., 2., 65)
+    for first_dense in (True, False):
+        if first_dense:
+            grid = np.concatenate((dense, sparse[1:]))
+            tl = np.concatenate((dense, sparse[[20, 64]]))
+        else:
+            grid = np.concatenate((dense, sparse[1:]))
+            tl = np.concatenate((dense[[0, 7, 64]], sparse[1:]))
+        (xs, _), (xg, _) = both(lambda: m.ornstein_uhlenbeck_process(
+            x0=.1, theta=lambda s: .2 + .1*s, k=1., sigma=.3, paths=paths, seed=12,
+            steps=grid, output='device'), tl)
+        same(xs, xg)
+        assert xs.x.shape[0] == tl.size and bool(torch.isfinite(xs.x).all())
+
+
 def test_stream_traced_sde():
     m = sd()
 
