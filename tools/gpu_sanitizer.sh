@@ -11,3 +11,6 @@ T=200 run mem_smoke $S --tool memcheck python -c "import __graft_entry__ as g; g
 T=420 run mem_stream_parity $S --tool memcheck python -m pytest tests/test_gpu_stream.py tests/test_gpu_parity.py -q -x
 T=300 run mem_edge_jit $S --tool memcheck python -m pytest tests/test_gpu_edge.py tests/test_gpu_jit.py -q -x
 T=420 run race_stream_parity $S --tool racecheck python -m pytest tests/test_gpu_stream.py tests/test_gpu_parity.py -q -x
+T=420 run mem_stats_dropin $S --tool memcheck python -m pytest tests/test_gpu_stats.py tests/test_gpu_dropin.py -q -x
+T=420 run race_stats_edge $S --tool racecheck python -m pytest tests/test_gpu_stats.py tests/test_gpu_edge.py -q -x
+T=300 run sync_stream_parity $S --tool synccheck python -m pytest tests/test_gpu_stream.py tests/test_gpu_parity.py -q -x
