@@ -181,8 +181,10 @@ int sdeb_device_info(int64_t* sm_count, int64_t* cc_major, int64_t* cc_minor,
 /* shapes, launch geometry and scratch requirement for a problem (host only).
  * SDEB_EINVAL (message naming the sizes) when the per-block shared memory the
  * problem needs -- parameter records staged per step block when time-dependent
- * (n_psteps > 1, not per path), the replay ring, in-kernel statistics -- exceeds
- * what an sm_100a block can have (227 KB, ~10 KB of it static). */
+ * (n_psteps > 1, not per path), the replay ring, in-kernel statistics, on top of
+ * the 72 KB of generator tables and the 32 KB alignment gap in front of them
+ * (records up to 28 KB live inside the gap) -- exceeds what an sm_100a block can
+ * have (227 KB, ~2 KB of it static). */
 int sdeb_plan(const sdeb_problem* p, sdeb_plan_t* plan);
 
 /* the fused integration launch (+ deterministic fold of the per-block
