@@ -65,6 +65,46 @@ def test_plan_shapes():
         _engine.problem_spec(_lib.MODEL_HESTON, 7, 1)
 
 
+def _plan(**kw):
+    p = _lib.Problem()
+    p.abi_version = _lib.ABI_VERSION
+    for k, v in dict(ncomp=1, noise=0, n_paths=10**6, pitch=10**6, n_steps=500, n_groups=1,
+                     n_rows=2, row0=0, n_psteps=1, params=0x1000, w0=0x1000, steps=0x1000,
+                     store_row=0x1000).items():
+        setattr(p, k, v)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    plan = _lib.Plan()
+    _lib.check(_lib.lib.sdeb_plan(ctypes.byref(p), ctypes.byref(plan)))
+    return plan
+
+
+def test_plan_kernel_choice_and_shared_memory_budget():
+    """Host-only sdeb_plan: which kernel a problem gets (0 general, 1 lean, 2 stream)
+    and that the dynamic shared memory -- 32 KB alignment gap + 72 KB generator
+    tables, staged records inside the gap -- leaves room for two blocks per SM
+    (233472 B per SM, 1 KB reserved + < 4 KB static per block) in the hot shapes."""
+    tables, gap, per_sm = 8*(2*256 + 2*256 + 2*64)*8, 32768, 233472
+    rec = np.zeros(16)
+    # north star: Heston, Philox, one time-invariant record, terminal statistics
+    lean = _plan(model=_lib.MODEL_HESTON, params_host=rec.ctypes.data, stats=0x1000,
+                 centre=0x1000, workspace=0x1000)
+    assert lean.kernel == 1 and lean.stats_in_kernel == 1
+    assert lean.smem_bytes == gap + tables + 2*1*8*8       # + the accumulators of 2 rows
+    # C2b: three correlated factors, time-dependent records, full paths stored
+    c2b = _plan(model=_lib.MODEL_HULL_WHITE, ncomp=3, n_psteps=500, n_rows=501, out=0x1000)
+    assert c2b.kernel == 2 and c2b.npt == 15
+    assert c2b.smem_bytes == gap + tables                  # 64 x 16 doubles live in the gap
+    # replayed increments: no generator tables, records + the cp.async ring
+    rep = _plan(model=_lib.MODEL_MEANREV, noise=1, dW=0x1000, n_rows=501, out=0x1000)
+    assert rep.kernel == 2 and rep.smem_bytes == 8*1*256*2*8
+    for plan in (lean, c2b):
+        assert 2*(plan.smem_bytes + 1024 + 4096) <= per_sm
+    # odd pitch: rows are not 16-byte aligned -> the general kernel
+    odd = _plan(model=_lib.MODEL_MEANREV, n_paths=999, pitch=999, n_rows=501, out=0x1000)
+    assert odd.kernel == 0
+
+
 def test_step_grid_and_sweeps_follow_reference():
     P = sd.ornstein_uhlenbeck_process(paths=3, steps=(0.1, .2, .21, .5, .93, 1.5))
     tt = np.array((0., .37, 1.))
