@@ -145,6 +145,28 @@ def test_stream_dense_and_sparse_step_blocks():
         assert xs.x.shape[0] == tl.size and bool(torch.isfinite(xs.x).all())
 
 
+def test_records_too_long_for_the_alignment_gap():
+    """Five correlated Heston pairs with time-dependent theta: 85 doubles per staged
+    record, 64 x 86 x 8 B = 44 KB per step block -- more than the 28 KB of the gap
+    in front of the generator tables, so both kernels place the records BEHIND
+    the tables (csrc/sde_engine.cuh: `front` / FRONT false; sdeb.cu adds the bytes)."""
+    m = sd()
+    rng = np.random.default_rng(5)
+    c = np.eye(10) + .1*rng.random((10, 10))
+    c = (c + c.T)/2
+    tl = np.linspace(0., 1., 81)                 # two step blocks
+    (xs, Ps), (xg, Pg) = both(lambda: m.full_heston_process(
+        vshape=(5,), x0=1., y0=.04, mu=.02, sigma=1., theta=lambda t: .04 + .01*t, k=2., xi=.4,
+        corr=c, paths=700, seed=8, output='device'), tl)
+    same(xs, xg)
+    assert torch.equal(Ps.info['negative_y_count'], Pg.info['negative_y_count'])
+    x, y = (np.asarray(z.x.cpu()) for z in xs)
+    assert np.isfinite(x).all() and (x > 0).all()
+    assert abs(y[-1].mean() - .0457) < .004      # y relaxes towards theta(t) from .04
+    zc = np.corrcoef(np.log(x[-1, 0]/x[-2, 0]), np.log(x[-1, 1]/x[-2, 1]))[0, 1]
+    assert abs(zc - c[0, 1]) < .12               # last-step log-returns carry corr
+
+
 def test_stream_traced_sde():
     m = sd()
 
